@@ -1,0 +1,185 @@
+"""Host-side operators: the reference's Python-visible surface, re-implemented over the C-ABI.
+
+torch is used for device memory and streams only (plumbing); all arithmetic happens in libfa_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+import importlib.util
+import math
+
+import torch
+
+from . import _lib
+from ._lib import FA_BF16, FA_F32, FaError, FaParams, check, lib
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return FA_F32
+    if t.dtype == torch.bfloat16:
+        return FA_BF16
+    raise FaError(f"unsupported dtype {t.dtype}: only float32 (tf32 tensor cores) and bfloat16")
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _shape4(Q, K, V):
+    if Q.dim() not in (3, 4) or K.dim() != Q.dim() or V.dim() != Q.dim():
+        raise FaError("expected Q, K, V as [B*H, N, d] or [B, H, N, d]")
+    if not (Q.is_cuda and K.is_cuda and V.is_cuda):
+        raise FaError("Q, K, V must be CUDA tensors: this operator has no CPU path")
+    if not (Q.dtype == K.dtype == V.dtype):
+        raise FaError("Q, K, V dtype mismatch")
+    if Q.dim() == 3:
+        b, h, nq, d = 1, Q.shape[0], Q.shape[1], Q.shape[2]
+        nk = K.shape[1]
+        ok = K.shape[0] == h and V.shape[0] == h and V.shape[1] == nk and K.shape[2] == d and V.shape[2] == d
+    else:
+        b, h, nq, d = Q.shape
+        nk = K.shape[2]
+        ok = K.shape[:2] == Q.shape[:2] and V.shape[:2] == Q.shape[:2] and V.shape[2] == nk and K.shape[3] == d and V.shape[3] == d
+    if not ok:
+        raise FaError(f"shape mismatch: Q {tuple(Q.shape)} K {tuple(K.shape)} V {tuple(V.shape)}")
+    return b, h, nq, nk, d
+
+
+def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False, impl=_lib.FA_IMPL_AUTO, out=None):
+    """O = softmax(scale * Q K^T [+ causal mask]) V.   scale defaults to 1/sqrt(d).
+
+    Q, K, V: contiguous CUDA tensors [B*H, N, d] or [B, H, N, d], float32 or bfloat16.
+    Returns O (same shape/dtype as Q; float32 if out_f32) and, if return_lse, LSE float32 [..., N].
+    """
+    b, h, nq, nk, d = _shape4(Q, K, V)
+    Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
+    if scale is None:
+        scale = 1.0 / math.sqrt(d)
+    with torch.cuda.device(Q.device):
+        o_dtype = torch.float32 if out_f32 else Q.dtype
+        O = out if out is not None else torch.empty(Q.shape, dtype=o_dtype, device=Q.device)
+        if out is not None and (O.shape != Q.shape or O.dtype != o_dtype or not O.is_contiguous()):
+            raise FaError("out tensor has the wrong shape/dtype or is not contiguous")
+        lse = torch.empty(Q.shape[:-1], dtype=torch.float32, device=Q.device) if return_lse else None
+        p = FaParams()
+        p.q, p.k, p.v, p.o = Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr()
+        p.lse = lse.data_ptr() if lse is not None else None
+        p.batch, p.heads, p.n_q, p.n_k, p.head_dim = b, h, nq, nk, d
+        p.dtype = _dtype_code(Q)
+        p.causal = 1 if causal else 0
+        p.o_f32 = 1 if (out_f32 and Q.dtype == torch.bfloat16) else 0
+        p.scale = float(scale)
+        p.q_stride_n = p.k_stride_n = p.v_stride_n = p.o_stride_n = d
+        p.q_stride_h, p.o_stride_h = nq * d, nq * d
+        p.k_stride_h = p.v_stride_h = nk * d
+        p.q_stride_b, p.o_stride_b = h * nq * d, h * nq * d
+        p.k_stride_b = p.v_stride_b = h * nk * d
+        p.impl = int(impl)
+        check(lib().fa_forward_ex(ctypes.byref(p), ctypes.c_void_p(_stream_ptr(Q.device))), "fa_forward_ex")
+    return (O, lse) if return_lse else O
+
+
+def forward(Q, K, V, causal=False):
+    """Reference operator `forward(Q_d, K_d, V_d, causal) -> O` (src/main.cpp:3; src/flashattention.cu:603-617).
+
+    Reference semantics: the scores are NOT scaled by 1/sqrt(d) (`scaling = 1.0`, src/flashattention.cu:593, 600).
+    Unlike the reference, inputs are validated, 4-D [B, H, N, d] is accepted as well as 3-D [B*H, N, d], the
+    launch is asynchronous on the current stream, and errors raise instead of being dropped.
+    """
+    return attention(Q, K, V, causal=bool(causal), scale=1.0)
+
+
+def attention_host(q, k, v, causal=False, scale=None, out=None):
+    """End-to-end call on HOST tensors (pinned or pageable): H2D copies, kernel, D2H copy, synchronise —
+    all inside libfa_b200.so (fa_forward_host).  Mirrors what bench_flashattention.py:31-33,70 does around forward()."""
+    if q.is_cuda or k.is_cuda or v.is_cuda:
+        raise FaError("attention_host takes host tensors")
+    if q.dim() == 3:
+        b, h, nq, d = 1, q.shape[0], q.shape[1], q.shape[2]
+        nk = k.shape[1]
+    else:
+        b, h, nq, d = q.shape
+        nk = k.shape[2]
+    if scale is None:
+        scale = 1.0 / math.sqrt(d)
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    o = out if out is not None else torch.empty_like(q)
+    check(lib().fa_forward_host(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), b, h, nq, nk, d, float(scale),
+                                1 if causal else 0, _dtype_code(q)), "fa_forward_host")
+    return o
+
+
+def attention_forward6(out, inp, B, T, C, NH, block_size=256, return_lse=False):
+    """llm.c-style entry (src/llm.c/attention_forward.cu:1106-1179): inp (B,T,3C) packed QKV fp32 on the device,
+    out (B,T,C); causal, scale 1/sqrt(C/NH).  The packed layout is consumed in place through strided TMA maps —
+    no permute/unpermute kernels, no temporaries.  `block_size` is accepted and ignored (it only sized the
+    reference's layout kernels)."""
+    if C % NH:
+        raise FaError("C must be divisible by NH")
+    hs = C // NH
+    if inp.dtype != torch.float32 or out.dtype != torch.float32 or not inp.is_cuda or not out.is_cuda:
+        raise FaError("attention_forward expects float32 CUDA tensors")
+    if inp.numel() != B * T * 3 * C or out.numel() != B * T * C or not inp.is_contiguous() or not out.is_contiguous():
+        raise FaError("attention_forward: bad tensor sizes")
+    with torch.cuda.device(inp.device):
+        lse = torch.empty((B, NH, T), dtype=torch.float32, device=inp.device) if return_lse else None
+        check(lib().fa_forward_packed_qkv(inp.data_ptr(), out.data_ptr(), lse.data_ptr() if lse is not None else None, B, T, NH, hs,
+                                          1.0 / math.sqrt(hs), 1, ctypes.c_void_p(_stream_ptr(inp.device))), "fa_forward_packed_qkv")
+    return (out, lse) if return_lse else out
+
+
+def attention_forward(kernel_num, out, inp, B, T, C, NH, block_size=256):
+    """Kernel-number dispatch of the llm.c harness (src/llm.c/attention_forward.cu:1183-1211).  Only kernel 6 — the
+    reference author's flash kernel — is on the hot path; 1-5 are upstream llm.c comparison kernels (out of scope)."""
+    if kernel_num != 6:
+        raise FaError("Invalid kernel number (only kernel 6, the flash attention kernel, is provided)")
+    return attention_forward6(out, inp, B, T, C, NH, block_size)
+
+
+def merge_partials(o_acc, lse_acc, o_new, lse_new):
+    """In-place log-sum-exp merge of two attention partials (fp32 O [..., d], fp32 LSE [...])."""
+    for t in (o_acc, lse_acc, o_new, lse_new):
+        if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+            raise FaError("merge_partials expects contiguous float32 CUDA tensors")
+    d = o_acc.shape[-1]
+    rows = o_acc.numel() // d
+    with torch.cuda.device(o_acc.device):
+        check(lib().fa_merge_partials(o_acc.data_ptr(), lse_acc.data_ptr(), o_new.data_ptr(), lse_new.data_ptr(), rows, d,
+                                      ctypes.c_void_p(_stream_ptr(o_acc.device))), "fa_merge_partials")
+    return o_acc, lse_acc
+
+
+def cast_to_bf16(src, dst=None):
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib().fa_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), ctypes.c_void_p(_stream_ptr(src.device))),
+              "fa_cast_f32_to_bf16")
+    return dst
+
+
+def last_impl() -> int:
+    return lib().fa_last_impl()
+
+
+def launch_count() -> int:
+    return lib().fa_launch_count()
+
+
+_ext = None
+
+
+def load_extension():
+    """The prebuilt pybind module with the reference's `forward(Q, K, V, causal)` (csrc/torch_binding.cpp) — what
+    `load(name='flash', sources=['src/main.cpp', 'src/flashattention.cu'])` returns in bench_flashattention.py:10."""
+    global _ext
+    if _ext is None:
+        so = _lib.PKG_DIR / "flash_b200.so"
+        if not so.exists():
+            raise FaError(f"{so} is missing: run `python flashattention.c_b200/build.py`")
+        lib()  # load libfa_b200.so first so the extension resolves it
+        spec = importlib.util.spec_from_file_location("flash_b200", str(so))
+        _ext = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_ext)
+    return _ext

@@ -1,0 +1,141 @@
+/*
+ * fa_b200.h — C-ABI of the B200-native FlashAttention forward (libfa_b200.so).
+ *
+ * Plain pointers and sizes only: no torch types, no C++ in the signatures.  Every entry
+ * point states the reference interface (file:line into kilianhae/FlashAttention.C) it
+ * stands in for.  All device entry points are asynchronous on `stream` (a cudaStream_t
+ * passed as void*; NULL = the legacy default stream) and return 0 on success or a negative
+ * fa_status code; fa_strerror() turns the code into text.  Nothing here ever falls back to
+ * a CPU path: without a usable sm_100 device the calls return FA_ERR_NO_DEVICE.
+ *
+ * Shapes: Q is [batch, heads, n_q, head_dim], K and V are [batch, heads, n_k, head_dim],
+ * O is [batch, heads, n_q, head_dim], LSE (optional) is [batch, heads, n_q] fp32 holding
+ * log(sum_j exp(scale * q.k_j)) per row.  The reference's 3-D [B*H, N, d] tensors
+ * (src/flashattention.cu:603-606) are the case batch = 1, heads = B*H.
+ */
+#ifndef FA_B200_H
+#define FA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FA_B200_VERSION 100 /* major*100 + minor */
+
+/* element type of Q, K, V (and of O unless stated otherwise) */
+enum fa_dtype {
+  FA_F32 = 0,  /* fp32 in HBM, contractions run as tcgen05 kind::tf32 (fp32 accumulate) */
+  FA_BF16 = 1  /* bf16 in HBM, contractions run as tcgen05 kind::f16  (fp32 accumulate) */
+};
+
+enum fa_status {
+  FA_OK = 0,
+  FA_ERR_INVALID_ARG = -1,   /* null pointer, non-positive size, unsupported head_dim ... */
+  FA_ERR_NO_DEVICE = -2,     /* no CUDA device, or the device is not sm_100 */
+  FA_ERR_CUDA = -3,          /* a CUDA runtime/driver call failed; see fa_last_cuda_error() */
+  FA_ERR_UNSUPPORTED = -4,   /* combination not implemented (e.g. misaligned strides) */
+  FA_ERR_ALIGNMENT = -5      /* pointer or stride not 16-byte aligned (TMA requirement) */
+};
+
+/* which kernel family served the most recent launch on this thread (fa_last_impl) */
+enum fa_impl {
+  FA_IMPL_NONE = 0,
+  FA_IMPL_TCGEN05 = 1,  /* TMA + tcgen05.mma + TMEM warp-specialised kernel (the product) */
+  FA_IMPL_SIMT = 2      /* CUDA-core general-shape kernel (odd head dims; the on-GPU checker) */
+};
+
+/* strided problem description.  Strides are in ELEMENTS; the head_dim axis is contiguous. */
+typedef struct fa_params {
+  const void* q; const void* k; const void* v;
+  void* o;                 /* same dtype as q unless o_f32 != 0 */
+  float* lse;              /* optional [batch, heads, n_q] contiguous fp32; may be NULL */
+  int64_t batch, heads, n_q, n_k;
+  int32_t head_dim;        /* tcgen05 path: 32, 64, 128 (bf16: 64, 128); SIMT path: 8..256, %8 == 0 */
+  int32_t dtype;           /* enum fa_dtype */
+  int32_t causal;          /* 0 / 1.  Causal is bottom-right aligned: key j visible to row i iff j <= i + (n_k - n_q) */
+  int32_t o_f32;           /* bf16 inputs only: write O as fp32 (used by the ring merge) */
+  float scale;             /* multiplies q.k before the softmax; the reference's torch path uses 1.0f
+                              (src/flashattention.cu:593), its llm.c path 1/sqrt(d) (src/llm.c/attention_forward.cu:1123) */
+  int64_t q_stride_b, q_stride_h, q_stride_n;
+  int64_t k_stride_b, k_stride_h, k_stride_n;
+  int64_t v_stride_b, v_stride_h, v_stride_n;
+  int64_t o_stride_b, o_stride_h, o_stride_n;
+  int32_t impl;            /* 0 = automatic; FA_IMPL_TCGEN05 / FA_IMPL_SIMT force a kernel family (tests) */
+  int32_t reserved;
+} fa_params;
+
+/*
+ * fa_forward — O = softmax(scale * Q K^T [+ causal mask]) V on contiguous [batch, heads, n, d].
+ * Replaces the launcher + kernel pair run_flash_tiled_coarse[_causal] -> flash_tiled_coarse[_causal]
+ * (src/flashattention.cu:590-602, 139-355, 359-579) behind forward() (src/flashattention.cu:603-617).
+ * Unlike the reference it does not synchronise the device and it reports launch errors.
+ */
+int fa_forward(const void* q, const void* k, const void* v, void* o, float* lse,
+               int64_t batch, int64_t heads, int64_t n_q, int64_t n_k, int32_t head_dim,
+               float scale, int32_t causal, int32_t dtype, void* stream);
+
+/* fa_forward_ex — the same through an explicit strided description (packed / head-interleaved layouts). */
+int fa_forward_ex(const fa_params* p, void* stream);
+
+/*
+ * fa_forward_packed_qkv — llm.c layout: inp is (B, T, 3, NH, hs) fp32, out is (B, T, NH, hs) fp32.
+ * Replaces permute_kernel -> flashattention -> unpermute_kernel -> D2D copy inside attention_forward6
+ * (src/llm.c/attention_forward.cu:1106-1179, 519-565, 881-1104): the strided views go straight into
+ * the TMA descriptors, so there is no temporary, no cudaMalloc and no layout pass.
+ */
+int fa_forward_packed_qkv(const float* inp, float* out, float* lse,
+                          int32_t B, int32_t T, int32_t NH, int32_t hs,
+                          float scale, int32_t causal, void* stream);
+
+/*
+ * fa_forward_host — the same operator with HOST buffers: copies Q, K, V to the device, runs
+ * fa_forward, copies O back and synchronises.  This is the end-to-end call bench.py times
+ * ("e2e"); it mirrors what bench_flashattention.py:31-33,70 does around forward().
+ * Device scratch is cached inside the library and reused between calls.
+ */
+int fa_forward_host(const void* q_host, const void* k_host, const void* v_host, void* o_host,
+                    int64_t batch, int64_t heads, int64_t n_q, int64_t n_k, int32_t head_dim,
+                    float scale, int32_t causal, int32_t dtype);
+
+/*
+ * fa_merge_partials — log-sum-exp merge of two attention partials over disjoint key sets, in place:
+ *   lse = log(exp(lse_acc) + exp(lse_new));  o_acc = o_acc*exp(lse_acc-lse) + o_new*exp(lse_new-lse)
+ * o_acc / o_new are fp32 [rows, head_dim] contiguous, lse_* fp32 [rows].  Used by the ring
+ * (sequence-partitioned) forward.  The reference plumbs `out_l` (src/flashattention.cu:140, 609)
+ * but never writes it; this is the consumer it was meant for.
+ */
+int fa_merge_partials(float* o_acc, float* lse_acc, const float* o_new, const float* lse_new,
+                      int64_t rows, int32_t head_dim, void* stream);
+
+/* fa_cast_f32_to_bf16 — final cast of the ring accumulator ([n] fp32 -> bf16). */
+int fa_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/*
+ * Reference-named shims (same argument order and meaning as the reference symbols).
+ *
+ * run_flash_tiled_coarse / _causal: test.cu:591-603 (torch-less launchers; note the O, K, Q, V order),
+ *   [batch, seq, 64] fp32, scale 1.0, synchronous like the reference.
+ * attention_forward6 / attention_forward: src/llm.c/attention_forward.cu:1106-1109 and 1183-1211.
+ *   Only kernel_num 6 (the author's flash kernel) is served; the llm.c comparison kernels 1-5 are out of
+ *   scope and, like an invalid number in the reference (1207-1209), print a message and exit(1).
+ *   Errors print and exit(EXIT_FAILURE) like cudaCheck (src/llm.c/common.h:16-23).
+ */
+void run_flash_tiled_coarse(float* O, float* K_d, float* Q_d, float* V_d, int batch_size, int seq_len);
+void run_flash_tiled_coarse_causal(float* O, float* K_d, float* Q_d, float* V_d, int batch_size, int seq_len);
+void attention_forward6(float* out, const float* inp, int B, int T, int C, int NH, const int block_size);
+void attention_forward(int kernel_num, float* out, float* vaccum, float* qkvr, float* preatt, float* att,
+                       const float* inp, int B, int T, int C, int NH, const int block_size);
+
+/* diagnostics */
+const char* fa_strerror(int status);
+const char* fa_last_cuda_error(void); /* text of the last CUDA failure seen by this thread ("" if none) */
+int fa_last_impl(void);               /* enum fa_impl of the last successful launch on this thread */
+int fa_version(void);
+int64_t fa_launch_count(void);        /* number of kernels this library has launched in this process */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FA_B200_H */
