@@ -323,6 +323,14 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         s[i + 1] = ex2(fmaf(s[i + 1], c, neg_mc));
         s[i + 2] = ex2(fmaf(s[i + 2], c, neg_mc));
         s[i + 3] = ex2(fmaf(s[i + 3], c, neg_mc));
+        if constexpr (kTF32) {
+          // kind::tf32 reads only the top 19 bits of P; sum exactly those values so that O = (sum P~ V) / (sum P~)
+          // is normalised by what the tensor core actually multiplied (removes the truncation bias from O)
+          s[i] = __uint_as_float(__float_as_uint(s[i]) & 0xFFFFE000u);
+          s[i + 1] = __uint_as_float(__float_as_uint(s[i + 1]) & 0xFFFFE000u);
+          s[i + 2] = __uint_as_float(__float_as_uint(s[i + 2]) & 0xFFFFE000u);
+          s[i + 3] = __uint_as_float(__float_as_uint(s[i + 3]) & 0xFFFFE000u);
+        }
         l0 += s[i];
         l1 += s[i + 1];
         l2 += s[i + 2];

@@ -1,0 +1,102 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/fa_b200.h declares,
+argument validation works without a device, and the host-side logic (sharding, ring schedule, error behaviour)."""
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "fa_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?(?:int|void|int64_t|char\s*\*|const char\s*\*)\s*\*?\s*(\w+)\s*\(", text, flags=re.M)
+    return sorted(set(names))
+
+
+def test_header_symbols_match_python_binding(fab):
+    from flashattention_c_b200 import _lib
+
+    declared = _declared_symbols()
+    assert declared, "could not parse include/fa_b200.h"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+
+
+def test_library_loads_and_exports_every_declared_symbol(fab):
+    L = fab.lib()
+    for name in _declared_symbols():
+        assert hasattr(L, name), f"libfa_b200.so does not export {name}"
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(ROOT / "flashattention.c_b200" / "libfa_b200.so")],
+                        capture_output=True, text=True, check=True).stdout
+    for name in _declared_symbols():
+        assert re.search(rf"\bT {name}\b", nm), f"{name} is not an unmangled (extern \"C\") export"
+
+
+def test_version_and_strerror(fab):
+    L = fab.lib()
+    assert L.fa_version() == 100
+    assert L.fa_strerror(0) == b"ok"
+    assert b"no CPU fallback" in L.fa_strerror(-2)
+    assert L.fa_strerror(-12345) == b"unknown status"
+
+
+def test_invalid_arguments_are_rejected_before_touching_a_device(fab):
+    L = fab.lib()
+    assert L.fa_forward(None, None, None, None, None, 1, 1, 16, 16, 64, 1.0, 0, 0, None) == -1   # null pointers
+    buf = (ctypes.c_float * 16)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert L.fa_forward(p, p, p, p, None, 1, 1, 0, 16, 64, 1.0, 0, 0, None) == -1                # n_q = 0
+    assert L.fa_forward(p, p, p, p, None, 1, 1, 16, 16, 64, 1.0, 0, 7, None) == -1               # bad dtype
+    assert L.fa_forward(p, p, p, p, None, 1, 1, 16, 16, 64, -1.0, 0, 0, None) == -1              # scale <= 0
+    assert L.fa_merge_partials(p, p, p, p, 4, 6, None) == -1                                     # head_dim % 4
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device behaviour")
+def test_no_device_is_an_error_not_a_fallback(fab):
+    L = fab.lib()
+    buf = (ctypes.c_float * 4096)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert L.fa_forward(p, p, p, p, None, 1, 1, 16, 16, 64, 1.0, 0, 0, None) == -2  # FA_ERR_NO_DEVICE
+    q = torch.zeros(2, 16, 64)
+    with pytest.raises(fab.FaError):
+        fab.forward(q, q, q, False)   # CPU tensors: the operator has no CPU path
+    with pytest.raises(fab.FaError):
+        fab.attention_host(q, q, q)    # host entry needs a device too
+
+
+def test_python_argument_checks(fab):
+    q = torch.zeros(2, 16, 64)
+    with pytest.raises(fab.FaError):
+        fab.attention(q, q[:, :, :32], q)          # shape mismatch / CPU tensors
+    with pytest.raises(fab.FaError):
+        fab.attention_forward(3, q, q, 1, 16, 64, 1)  # kernels 1-5 of the llm.c harness are out of scope
+
+
+def test_bh_shard_range_covers_everything_once(fab):
+    for total in (1, 7, 16, 128, 129):
+        for world in (1, 2, 4, 8):
+            seen = []
+            for r in range(world):
+                s, e = fab.bh_shard_range(total, r, world)
+                assert 0 <= s <= e <= total
+                seen += list(range(s, e))
+            assert seen == list(range(total))
+
+
+def test_ring_schedule_visits_every_shard_once():
+    from flashattention_c_b200.ring import ring_schedule
+
+    for world in (1, 2, 4, 8):
+        for r in range(world):
+            sched = ring_schedule(r, world)
+            assert [s for s, _ in sched] == list(range(world))
+            assert sched[0][1] == r                     # step 0 is the local shard
+            assert sorted(src for _, src in sched) == list(range(world))
+        # what rank r holds at step s is what rank r-1 held at step s-1 (send to r+1, receive from r-1)
+        for s in range(1, world):
+            for r in range(world):
+                assert ring_schedule(r, world)[s][1] == ring_schedule((r - 1) % world, world)[s - 1][1]
