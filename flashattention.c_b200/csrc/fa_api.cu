@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -167,6 +168,33 @@ int run_tc(const fa_params* p, cudaStream_t st) {
   fp.num_m_blocks = (int)((p->n_q + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM));
   fp.lse = p->lse;
   fp.v_desc_hi = fa::make_sdesc_hi(v_lbo, v_sbo, v_layout);
+  fp.trace = nullptr;
+#if FA_TRACE
+  // tracing build: record CTA 0's pipeline timeline and dump it (synchronously) to $FA_B200_TRACE after the launch
+  static unsigned long long* d_trace = nullptr;
+  const char* trace_path = getenv("FA_B200_TRACE");
+  const size_t trace_n = 4 * fa::kTraceSteps * 8;
+  if (trace_path) {
+    if (!d_trace) FA_CUDA(cudaMalloc(&d_trace, trace_n * sizeof(unsigned long long)));
+    FA_CUDA(cudaMemsetAsync(d_trace, 0, trace_n * sizeof(unsigned long long), st));
+    fp.trace = d_trace;
+  }
+  struct TraceDump {
+    const char* path; unsigned long long* dev; size_t n; cudaStream_t st;
+    ~TraceDump() {
+      if (!path) return;
+      cudaStreamSynchronize(st);
+      unsigned long long* h = (unsigned long long*)malloc(n * sizeof(unsigned long long));
+      cudaMemcpy(h, dev, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      FILE* f = fopen(path, "w");
+      if (f) {
+        for (size_t i = 0; i < n; ++i) fprintf(f, "%llu%c", h[i], (i % 8 == 7) ? '\n' : ' ');
+        fclose(f);
+      }
+      free(h);
+    }
+  } trace_dump{trace_path, d_trace, trace_n, st};
+#endif
   const bool c = p->causal != 0;
   if (!bf16) {
     if (p->head_dim == 32) return launch_tc_c<true, 32, false>(c, mq, mk, mv, mo, fp, st);
@@ -221,8 +249,14 @@ void fill_contiguous(fa_params* p, const void* q, const void* k, const void* v, 
   p->o_stride_n = d; p->o_stride_h = n_q * d; p->o_stride_b = heads * n_q * d;
 }
 
-// cached device scratch for fa_forward_host
-struct HostScratch { void* q = nullptr; void* k = nullptr; void* v = nullptr; void* o = nullptr; size_t cap_q = 0, cap_kv = 0, cap_o = 0; cudaStream_t st = nullptr; };
+// cached device scratch + streams for fa_forward_host
+constexpr int kHostMaxChunks = 8;
+struct HostScratch {
+  void* q = nullptr; void* k = nullptr; void* v = nullptr; void* o = nullptr;
+  size_t cap_q = 0, cap_kv = 0, cap_o = 0;
+  cudaStream_t st_in = nullptr, st_run = nullptr, st_out = nullptr;
+  cudaEvent_t ev_in[kHostMaxChunks] = {}, ev_run[kHostMaxChunks] = {};
+};
 HostScratch g_hs;
 std::mutex g_hs_mu;
 
@@ -307,7 +341,15 @@ int fa_forward_host(const void* qh, const void* kh, const void* vh, void* oh, in
   const size_t bq = (size_t)batch * heads * n_q * head_dim * es, bkv = (size_t)batch * heads * n_k * head_dim * es;
   std::lock_guard<std::mutex> lk(g_hs_mu);
   HostScratch& s = g_hs;
-  if (!s.st) FA_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+  if (!s.st_in) {
+    FA_CUDA(cudaStreamCreateWithFlags(&s.st_in, cudaStreamNonBlocking));
+    FA_CUDA(cudaStreamCreateWithFlags(&s.st_run, cudaStreamNonBlocking));
+    FA_CUDA(cudaStreamCreateWithFlags(&s.st_out, cudaStreamNonBlocking));
+    for (int i = 0; i < kHostMaxChunks; ++i) {
+      FA_CUDA(cudaEventCreateWithFlags(&s.ev_in[i], cudaEventDisableTiming));
+      FA_CUDA(cudaEventCreateWithFlags(&s.ev_run[i], cudaEventDisableTiming));
+    }
+  }
   if (s.cap_q < bq) {
     if (s.q) cudaFree(s.q);
     s.q = nullptr; s.cap_q = 0;
@@ -328,13 +370,30 @@ int fa_forward_host(const void* qh, const void* kh, const void* vh, void* oh, in
     FA_CUDA(cudaMalloc(&s.v, bkv));
     s.cap_kv = bkv;
   }
-  FA_CUDA(cudaMemcpyAsync(s.q, qh, bq, cudaMemcpyHostToDevice, s.st));
-  FA_CUDA(cudaMemcpyAsync(s.k, kh, bkv, cudaMemcpyHostToDevice, s.st));
-  FA_CUDA(cudaMemcpyAsync(s.v, vh, bkv, cudaMemcpyHostToDevice, s.st));
-  rc = fa_forward(s.q, s.k, s.v, s.o, nullptr, batch, heads, n_q, n_k, head_dim, scale, causal, dtype, s.st);
-  if (rc) return rc;
-  FA_CUDA(cudaMemcpyAsync(oh, s.o, bq, cudaMemcpyDeviceToHost, s.st));
-  FA_CUDA(cudaStreamSynchronize(s.st));
+  // Every (batch, head) is independent, so the copy-in, the kernel and the copy-out are pipelined over chunks of
+  // the flattened batch*heads axis on three streams: H2D of chunk g+1 and D2H of chunk g-1 overlap the kernel of g.
+  const int64_t bh = batch * heads;
+  int chunks = (int)std::min<int64_t>(bh, kHostMaxChunks);
+  if ((bq + 2 * bkv) / chunks < (4u << 20)) chunks = (int)std::max<int64_t>(1, std::min<int64_t>(bh, (int64_t)((bq + 2 * bkv) >> 22)));
+  const int64_t per = (bh + chunks - 1) / chunks;
+  const size_t row_q = (size_t)n_q * head_dim * es, row_kv = (size_t)n_k * head_dim * es;
+  int g = 0;
+  for (int64_t h0 = 0; h0 < bh; h0 += per, ++g) {
+    const int64_t nh = std::min<int64_t>(per, bh - h0);
+    char* dq = (char*)s.q + h0 * row_q; char* dk = (char*)s.k + h0 * row_kv; char* dv = (char*)s.v + h0 * row_kv;
+    char* dout = (char*)s.o + h0 * row_q;
+    FA_CUDA(cudaMemcpyAsync(dq, (const char*)qh + h0 * row_q, nh * row_q, cudaMemcpyHostToDevice, s.st_in));
+    FA_CUDA(cudaMemcpyAsync(dk, (const char*)kh + h0 * row_kv, nh * row_kv, cudaMemcpyHostToDevice, s.st_in));
+    FA_CUDA(cudaMemcpyAsync(dv, (const char*)vh + h0 * row_kv, nh * row_kv, cudaMemcpyHostToDevice, s.st_in));
+    FA_CUDA(cudaEventRecord(s.ev_in[g], s.st_in));
+    FA_CUDA(cudaStreamWaitEvent(s.st_run, s.ev_in[g], 0));
+    rc = fa_forward(dq, dk, dv, dout, nullptr, 1, nh, n_q, n_k, head_dim, scale, causal, dtype, s.st_run);
+    if (rc) return rc;
+    FA_CUDA(cudaEventRecord(s.ev_run[g], s.st_run));
+    FA_CUDA(cudaStreamWaitEvent(s.st_out, s.ev_run[g], 0));
+    FA_CUDA(cudaMemcpyAsync((char*)oh + h0 * row_q, dout, nh * row_q, cudaMemcpyDeviceToHost, s.st_out));
+  }
+  FA_CUDA(cudaStreamSynchronize(s.st_out));
   return FA_OK;
 }
 

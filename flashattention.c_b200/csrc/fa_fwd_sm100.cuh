@@ -12,8 +12,12 @@
 // tensor pipe: while the softmax warps of one tile work on S_j, the MMA thread runs P*V and the next
 // Q*K^T of the other tile.
 //
-// Warp roles (320 threads): warps 0-3 softmax/epilogue of tile A, 4-7 of tile B (warp w reads TMEM lanes
-// 32*(w%4)..+31), warp 8 lane 0 = TMA producer (+ TMEM alloc/dealloc by the whole warp), warp 9 lane 0 = MMA issuer.
+// Warp roles (352 threads): warps 0-3 softmax/epilogue of tile A, 4-7 of tile B (warp w reads TMEM lanes
+// 32*(w%4)..+31), warp 8 lane 0 = TMA producer (+ TMEM alloc/dealloc by the whole warp), warps 9 and 10 = MMA
+// issuers of tile A and tile B (one elected lane each).  One issuer per tile matters: `tcgen05.mma` issue
+// back-pressures at the rate the tensor pipe retires (~64 cycles per 128x128x16 MMA) and every mbarrier
+// wait + tcgen05 fence costs ~200 cycles even when already complete, so with a single issuer thread all of its
+// waiting shows up as tensor-pipe idle time (measured: profiles/r01_trace_v1_c4_report.txt).
 //
 // TMEM columns (512 allocated): S_A [0,128)  S_B [128,256)  O_A [256,256+d)  O_B [256+d, 256+2d).
 // P aliases S: bf16 path packs two bf16 per column into S cols [0,64); tf32 path overwrites S in place.
@@ -22,6 +26,38 @@
 // boxes of [128 rows x 128 bytes] in the SWIZZLE_128B layout that TMA writes and the UMMA descriptors read.
 #pragma once
 #include "ptx.cuh"
+
+// bring-up / tuning switches (A/B-tested on hardware; the defaults are what ships)
+#ifndef FA_OPT_SPLITP
+#define FA_OPT_SPLITP 1   // deliver P to the MMA thread in two 64-key halves so P*V overlaps the second half of the exps
+#endif
+#ifndef FA_OPT_LDPIPE
+#define FA_OPT_LDPIPE 0   // overlap the row-max pass with the remaining tcgen05.ld of the S row
+#endif
+#ifndef FA_OPT_F2
+#define FA_OPT_F2 1       // packed FFMA2 / FADD2 for the scale-subtract and the row sum (bf16 instances only: in the tf32
+                          // instances the per-element P truncation breaks register pairing and costs ~150 extra moves)
+#endif
+#ifndef FA_OPT_ISSUERS
+#define FA_OPT_ISSUERS 1  // MMA-issuer warps: 2 = one per Q tile (independent), 1 = one warp issuing A then B in order
+#endif
+#ifndef FA_OPT_STAGGER
+#define FA_OPT_STAGGER 0  // (2 issuers) start tile B half a step late so the two tiles run in anti-phase
+#endif
+// -DFA_TRACE=1 builds a timeline-tracing kernel: CTA 0 records clock64() at every pipeline hand-off of its first
+// kTraceSteps KV tiles into FwdParams::trace ([role 0..3][step][slot 0..7]); see scripts/trace_report.py.
+#ifndef FA_TRACE
+#define FA_TRACE 0
+#endif
+#if FA_TRACE
+#define FA_TRACE_AT(role, step, slot)                                                                      \
+  do {                                                                                                      \
+    if (p.trace != nullptr && blockIdx.x == 0 && (step) < fa::kTraceSteps && ((role) < 2 || (threadIdx.x & 31) == 0)) \
+      p.trace[((role) * fa::kTraceSteps + (step)) * 8 + (slot)] = static_cast<unsigned long long>(clock64()); \
+  } while (0)
+#else
+#define FA_TRACE_AT(role, step, slot) do { } while (0)
+#endif
 
 namespace fa {
 
@@ -33,12 +69,14 @@ struct FwdParams {
   int num_m_blocks;   // ceil(n_q / 256)
   float* lse;         // [batch, heads, n_q] or nullptr
   uint64_t v_desc_hi; // upper descriptor bits (LBO/SBO/layout) of V as the MN-major B operand of P*V
+  unsigned long long* trace;  // FA_TRACE builds only; nullptr otherwise
 };
+constexpr int kTraceSteps = 48;
 
 constexpr int kBlockM = 128;          // rows per Q tile
 constexpr int kBlockN = 128;          // keys per K/V tile
 constexpr int kChunkBytes = 128 * 128;  // one TMA box: 128 rows x 128 bytes
-constexpr int kNumThreads = 320;
+constexpr int kNumThreads = 352;      // 8 softmax warps + TMA producer + one MMA-issuer warp per Q tile
 constexpr float kRescaleThreshold = 8.0f;  // lazy rescale: keep a stale max while it is within 2^8
 
 template <bool kTF32, int kHeadDim, bool kOutF32>
@@ -53,7 +91,7 @@ struct FwdTraits {
   static constexpr int kNBuf = kDChunks == 1 ? 8 : 5;          // K/V ring depth (tiles)
   static constexpr int kUmmaK = 32 / kInSize;                  // K per tcgen05.mma: 8 (tf32) / 16 (bf16)
   static constexpr int kSmemData = (2 + kNBuf) * kTileBytes;
-  static constexpr int kNumBarriers = 2 /*q*/ + 2 * kNBuf + 2 /*s_full*/ + 2 /*p_full*/ + 2 /*o_final*/;
+  static constexpr int kNumBarriers = 2 /*q*/ + 2 * kNBuf + 2 /*s_full*/ + 4 /*p_full halves*/ + 2 /*o_final*/;
   static constexpr int kSmemBytes = kSmemData + kNumBarriers * 8 + 16 /*tmem ptr*/ + 1024 /*alignment slack*/;
   static constexpr int kTmemS = 0;        // + 128*t
   static constexpr int kTmemO = 256;      // + kHeadDim*t
@@ -81,8 +119,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const uint32_t bar_full = sBar + 16;                  // [kNBuf]
   const uint32_t bar_empty = bar_full + 8 * T::kNBuf;   // [kNBuf]
   const uint32_t bar_s = bar_empty + 8 * T::kNBuf;      // [2]
-  const uint32_t bar_p = bar_s + 16;                    // [2]
-  const uint32_t bar_o = bar_p + 16;                    // [2]
+  const uint32_t bar_p = bar_s + 16;                    // [tile][half] = [4]
+  const uint32_t bar_o = bar_p + 32;                    // [2]
   const uint32_t s_tmem_ptr = bar_o + 16;
 
   const int warp = threadIdx.x >> 5;
@@ -117,13 +155,15 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (warp == 9 && lane == 0) {
     mbar_init(bar_q, 1);
     mbar_init(bar_q + 8, 1);
+    const uint32_t n_active = (n_tile[0] > 0 ? 1u : 0u) + (n_tile[1] > 0 ? 1u : 0u);
     for (int i = 0; i < T::kNBuf; ++i) {
       mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, (FA_OPT_ISSUERS == 2 && n_active > 0) ? n_active : 1u);   // every issuer releases the slot
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar_s + 8 * t, 1);
-      mbar_init(bar_p + 8 * t, 128);
+      mbar_init(bar_p + 16 * t, 128);
+      mbar_init(bar_p + 16 * t + 8, 128);
       mbar_init(bar_o + 8 * t, 1);
     }
     fence_mbar_init();
@@ -171,9 +211,13 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                       head, batch);
       }
     }
-  } else if (warp == 9) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0 && n_max > 0) {
+  } else if (warp == 9 || warp == 10) {
+    // =========================== MMA issuer(s) ===========================
+    // The whole warp follows the control flow (so every branch is warp-uniform); one elected lane issues.
+#if FA_OPT_ISSUERS == 2
+    const int t = warp - 9;
+    const int n_mine = n_tile[t];
+    if (n_mine > 0) {
       constexpr uint32_t kFmt = kTF32 ? 2u : 1u;
       constexpr uint32_t idesc_s = make_idesc(kFmt, 0, kBlockM, kBlockN);
       constexpr uint32_t idesc_pv = make_idesc(kFmt, 1, kBlockM, kHeadDim);
@@ -186,71 +230,194 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const uint64_t hi_mnmajor = p.v_desc_hi;
       constexpr int kKStepsS = kHeadDim / T::kUmmaK;   // k-steps of Q K^T (32 bytes each)
       constexpr int kKStepsPV = kBlockN / T::kUmmaK;   // k-steps of P V (UmmaK keys each)
+      const uint32_t tmem_s = tmem_base + T::kTmemS + t * kBlockN;   // S_t, and P_t which aliases it
+      const uint32_t tmem_o = tmem_base + T::kTmemO + t * kHeadDim;
+      const uint64_t qd = sdesc_at(hi_kmajor, sQ + t * T::kTileBytes);
 
-      auto issue_s = [&](int t, int buf) {
-        const uint32_t qa = sQ + t * T::kTileBytes;
-        const uint32_t kb = sKV + buf * T::kTileBytes;
-        const uint32_t d = tmem_base + T::kTmemS + t * kBlockN;
+      // Descriptors are built once per operand tile; a k-step only adds to the 14-bit start-address field
+      // ((bytes >> 4); SMEM addresses are < 2^18, so the field never carries).
+      auto issue_s = [&](int buf) {
+        const uint64_t kd = sdesc_at(hi_kmajor, sKV + buf * T::kTileBytes);
 #pragma unroll
         for (int kk = 0; kk < kKStepsS; ++kk) {
-          const uint32_t off = (kk >> 2) * kChunkBytes + (kk & 3) * 32;
-          mma_ss<kTF32>(d, sdesc_at(hi_kmajor, qa + off), sdesc_at(hi_kmajor, kb + off), idesc_s, kk > 0 ? 1u : 0u);
+          const uint32_t off16 = ((kk >> 2) * kChunkBytes + (kk & 3) * 32) >> 4;
+          mma_ss<kTF32>(tmem_s, qd + off16, kd + off16, idesc_s, kk > 0 ? 1u : 0u);
         }
       };
-      auto issue_pv = [&](int t, int buf, bool accumulate) {
-        const uint32_t vb = sKV + buf * T::kTileBytes;
-        const uint32_t d = tmem_base + T::kTmemO + t * kHeadDim;
-        const uint32_t a = tmem_base + T::kTmemS + t * kBlockN;  // P aliases S
+      // P*V for k-steps [ks0, ks1) of the 128-key tile
+      auto issue_pv = [&](int buf, bool accumulate, int ks0, int ks1) {
+        const uint64_t vd = sdesc_at(hi_mnmajor, sKV + buf * T::kTileBytes);
 #pragma unroll
-        for (int ks = 0; ks < kKStepsPV; ++ks) {
-          mma_ts<kTF32>(d, a + ks * 8, sdesc_at(hi_mnmajor, vb + ks * (T::kUmmaK * 128)), idesc_pv,
+        for (int ks = ks0; ks < ks1; ++ks) {
+          mma_ts<kTF32>(tmem_o, tmem_s + ks * 8, vd + static_cast<uint32_t>(ks * (T::kUmmaK * 128 / 16)), idesc_pv,
                         (accumulate || ks > 0) ? 1u : 0u);
         }
       };
 
-      if (n_tile[0] > 0) mbar_wait(bar_q, 0, TAG_Q_FULL);
-      if (n_tile[1] > 0) mbar_wait(bar_q + 8, 0, TAG_Q_FULL);
+      mbar_wait(bar_q + 8 * t, 0, TAG_Q_FULL);
+#if FA_OPT_STAGGER
+      // anti-phase start: tile B's first S is issued only when tile A's softmax is half-way through its first tile
+      if (t == 1 && n_tile[0] > 1) mbar_wait(bar_p + (FA_OPT_SPLITP ? 0 : 8), 0, TAG_P_FULL);
+#endif
       // prologue: S_t(0) = Q_t K_0^T
       mbar_wait(bar_full + 0, 0, TAG_KV_FULL);
       tc_fence_after();
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (n_tile[t] > 0) {
-          issue_s(t, 0);
-          tc_commit(bar_s + 8 * t);
-        }
+      if (elect_one_sync()) {
+        issue_s(0);
+        tc_commit(bar_s + 8 * t);
+        tc_commit(bar_empty + 0);
       }
-      tc_commit(bar_empty + 0);
+      __syncwarp();
 
-      for (int j = 0; j < n_max; ++j) {
+      for (int j = 0; j < n_mine; ++j) {
         const int iv = 2 * j + 1;   // ring index of V_j
         const int ik = 2 * j + 2;   // ring index of K_{j+1}
         const int vbuf = iv % T::kNBuf;
         const int kbuf = ik % T::kNBuf;
+        const bool last = (j == n_mine - 1);
         mbar_wait(bar_full + 8 * vbuf, (iv / T::kNBuf) & 1, TAG_KV_FULL);
-        bool k_ready = false;
+        tc_fence_after();
+#if FA_OPT_SPLITP
+        FA_TRACE_AT(2 + t, j, 0);
+        mbar_wait(bar_p + 16 * t, j & 1, TAG_P_FULL);          // keys [0, 64) of P are in TMEM
+        tc_fence_after();
+        FA_TRACE_AT(2 + t, j, 1);
+        if (elect_one_sync()) issue_pv(vbuf, j > 0, 0, kKStepsPV / 2);
+        __syncwarp();
+        FA_TRACE_AT(2 + t, j, 2);
+        mbar_wait(bar_p + 16 * t + 8, j & 1, TAG_P_FULL);      // keys [64, 128)
+        tc_fence_after();
+        FA_TRACE_AT(2 + t, j, 3);
+        if (elect_one_sync()) {
+          issue_pv(vbuf, j > 0, kKStepsPV / 2, kKStepsPV);
+          if (last) tc_commit(bar_o + 8 * t);
+          tc_commit(bar_empty + 8 * vbuf);
+        }
+        __syncwarp();
+        FA_TRACE_AT(2 + t, j, 4);
+#else
+        FA_TRACE_AT(2 + t, j, 0);
+        mbar_wait(bar_p + 16 * t + 8, j & 1, TAG_P_FULL);
+        tc_fence_after();
+        FA_TRACE_AT(2 + t, j, 3);
+        if (elect_one_sync()) {
+          issue_pv(vbuf, j > 0, 0, kKStepsPV);
+          if (last) tc_commit(bar_o + 8 * t);
+          tc_commit(bar_empty + 8 * vbuf);
+        }
+        __syncwarp();
+        FA_TRACE_AT(2 + t, j, 4);
+#endif
+        if (!last) {
+          mbar_wait(bar_full + 8 * kbuf, (ik / T::kNBuf) & 1, TAG_KV_FULL);
+          tc_fence_after();
+          FA_TRACE_AT(2 + t, j, 5);
+          if (elect_one_sync()) {
+            issue_s(kbuf);
+            tc_commit(bar_s + 8 * t);
+            tc_commit(bar_empty + 8 * kbuf);
+          }
+          __syncwarp();
+          FA_TRACE_AT(2 + t, j, 6);
+        }
+      }
+      // K/V tiles this Q tile does not need (causal: the other tile reaches one tile further) still need this
+      // issuer's release; follow the ring in order (wait full, then arrive) so a slot is never released early.
+      if (lane == 0) {
+        for (int i = 2 * n_mine; i < 2 * n_max; ++i) {
+          const int buf = i % T::kNBuf;
+          mbar_wait(bar_full + 8 * buf, (i / T::kNBuf) & 1, TAG_KV_FULL);
+          mbar_arrive(bar_empty + 8 * buf);
+        }
+      }
+      __syncwarp();
+    }
+#else   // ---------------- FA_OPT_ISSUERS == 1: warp 9 issues for both tiles, A then B, in order ----------------
+    if (warp == 9 && n_max > 0) {
+      constexpr uint32_t kFmt = kTF32 ? 2u : 1u;
+      constexpr uint32_t idesc_s = make_idesc(kFmt, 0, kBlockM, kBlockN);
+      constexpr uint32_t idesc_pv = make_idesc(kFmt, 1, kBlockM, kHeadDim);
+      constexpr uint64_t hi_kmajor = make_sdesc_hi_sw128(16, 1024);
+      const uint64_t hi_mnmajor = p.v_desc_hi;
+      constexpr int kKStepsS = kHeadDim / T::kUmmaK;
+      constexpr int kKStepsPV = kBlockN / T::kUmmaK;
+      auto issue_s = [&](int t, int buf) {
+        const uint64_t qd = sdesc_at(hi_kmajor, sQ + t * T::kTileBytes);
+        const uint64_t kd = sdesc_at(hi_kmajor, sKV + buf * T::kTileBytes);
+        const uint32_t d = tmem_base + T::kTmemS + t * kBlockN;
+#pragma unroll
+        for (int kk = 0; kk < kKStepsS; ++kk) {
+          const uint32_t off16 = ((kk >> 2) * kChunkBytes + (kk & 3) * 32) >> 4;
+          mma_ss<kTF32>(d, qd + off16, kd + off16, idesc_s, kk > 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int t, int buf, bool accumulate, int ks0, int ks1) {
+        const uint64_t vd = sdesc_at(hi_mnmajor, sKV + buf * T::kTileBytes);
+        const uint32_t d = tmem_base + T::kTmemO + t * kHeadDim;
+        const uint32_t a = tmem_base + T::kTmemS + t * kBlockN;
+#pragma unroll
+        for (int ks = ks0; ks < ks1; ++ks) {
+          mma_ts<kTF32>(d, a + ks * 8, vd + static_cast<uint32_t>(ks * (T::kUmmaK * 128 / 16)), idesc_pv,
+                        (accumulate || ks > 0) ? 1u : 0u);
+        }
+      };
+      if (n_tile[0] > 0) mbar_wait(bar_q, 0, TAG_Q_FULL);
+      if (n_tile[1] > 0) mbar_wait(bar_q + 8, 0, TAG_Q_FULL);
+      mbar_wait(bar_full + 0, 0, TAG_KV_FULL);
+      tc_fence_after();
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (n_tile[t] > 0) {
+            issue_s(t, 0);
+            tc_commit(bar_s + 8 * t);
+          }
+        }
+        tc_commit(bar_empty + 0);
+      }
+      __syncwarp();
+      for (int j = 0; j < n_max; ++j) {
+        const int iv = 2 * j + 1, ik = 2 * j + 2;
+        const int vbuf = iv % T::kNBuf, kbuf = ik % T::kNBuf;
+        mbar_wait(bar_full + 8 * vbuf, (iv / T::kNBuf) & 1, TAG_KV_FULL);
+        if (j + 1 < n_max) mbar_wait(bar_full + 8 * kbuf, (ik / T::kNBuf) & 1, TAG_KV_FULL);
+        tc_fence_after();
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           if (j < n_tile[t]) {
-            mbar_wait(bar_p + 8 * t, j & 1, TAG_P_FULL);
+            const bool last = (j == n_tile[t] - 1);
+#if FA_OPT_SPLITP
+            FA_TRACE_AT(2 + t, j, 0);
+            mbar_wait(bar_p + 16 * t, j & 1, TAG_P_FULL);
             tc_fence_after();
-            issue_pv(t, vbuf, j > 0);
-            if (j == n_tile[t] - 1) tc_commit(bar_o + 8 * t);
-            if (j + 1 < n_tile[t]) {
-              if (!k_ready) {
-                mbar_wait(bar_full + 8 * kbuf, (ik / T::kNBuf) & 1, TAG_KV_FULL);
-                tc_fence_after();
-                k_ready = true;
+            FA_TRACE_AT(2 + t, j, 1);
+            if (elect_one_sync()) issue_pv(t, vbuf, j > 0, 0, kKStepsPV / 2);
+            __syncwarp();
+            FA_TRACE_AT(2 + t, j, 2);
+#endif
+            mbar_wait(bar_p + 16 * t + 8, j & 1, TAG_P_FULL);
+            tc_fence_after();
+            FA_TRACE_AT(2 + t, j, 3);
+            if (elect_one_sync()) {
+              issue_pv(t, vbuf, j > 0, FA_OPT_SPLITP ? kKStepsPV / 2 : 0, kKStepsPV);
+              if (last) tc_commit(bar_o + 8 * t);
+              if (!last) {
+                issue_s(t, kbuf);
+                tc_commit(bar_s + 8 * t);
               }
-              issue_s(t, kbuf);
-              tc_commit(bar_s + 8 * t);
             }
+            __syncwarp();
+            FA_TRACE_AT(2 + t, j, 6);
           }
         }
-        tc_commit(bar_empty + 8 * vbuf);
-        if (j + 1 < n_max) tc_commit(bar_empty + 8 * kbuf);
+        if (elect_one_sync()) {
+          tc_commit(bar_empty + 8 * vbuf);
+          if (j + 1 < n_max) tc_commit(bar_empty + 8 * kbuf);
+        }
+        __syncwarp();
       }
     }
+#endif
   } else {
     // =========================== softmax + epilogue (warps 0-7) ===========================
     const int t = warp >> 2;                       // Q tile of this warpgroup
@@ -265,33 +432,58 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     float m = -INFINITY;  // running (possibly stale) row max, in raw q.k units
     float l = 0.f;        // running row sum of exp2((s - m) * c)
 
+    const bool tracer = (warp & 3) == 0 && lane == 0;
+    (void)tracer;
     for (int j = 0; j < n_mine; ++j) {
+      if (tracer) FA_TRACE_AT(t, j, 0);
       mbar_wait(bar_s + 8 * t, j & 1, TAG_S_FULL);
       tc_fence_after();
+      if (tracer) FA_TRACE_AT(t, j, 1);
       float s[128];
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) tmem_ld32(tS + q4 * 32, reinterpret_cast<uint32_t*>(&s[q4 * 32]));
-      tc_wait_ld();
-
       // masking: key kv0 + i is visible iff i <= limit
       const int kv0 = j * kBlockN;
       int limit = p.n_k - 1 - kv0;
       if (kCausal) limit = min(limit, q_row + p.causal_offset - kv0);
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#if FA_OPT_LDPIPE
+      // chunk q's row-max pass runs while chunk q+1 is still in flight from TMEM
+      tmem_ld32(tS, reinterpret_cast<uint32_t*>(&s[0]));
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        tc_wait_ld();
+        if (q4 < 3) tmem_ld32(tS + (q4 + 1) * 32, reinterpret_cast<uint32_t*>(&s[(q4 + 1) * 32]));
+        if (limit < kBlockN - 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (q4 * 32 + i > limit) s[q4 * 32 + i] = -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = fmaxf(mx0, s[q4 * 32 + i]);
+          mx1 = fmaxf(mx1, s[q4 * 32 + i + 1]);
+          mx2 = fmaxf(mx2, s[q4 * 32 + i + 2]);
+          mx3 = fmaxf(mx3, s[q4 * 32 + i + 3]);
+        }
+      }
+#else
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) tmem_ld32(tS + q4 * 32, reinterpret_cast<uint32_t*>(&s[q4 * 32]));
+      tc_wait_ld();
       if (limit < kBlockN - 1) {
 #pragma unroll
         for (int i = 0; i < 128; ++i)
           if (i > limit) s[i] = -INFINITY;
       }
-
-      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
 #pragma unroll
-      for (int i = 4; i < 128; i += 4) {
+      for (int i = 0; i < 128; i += 4) {
         mx0 = fmaxf(mx0, s[i]);
         mx1 = fmaxf(mx1, s[i + 1]);
         mx2 = fmaxf(mx2, s[i + 2]);
         mx3 = fmaxf(mx3, s[i + 3]);
       }
+#endif
       const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+      if (tracer) FA_TRACE_AT(t, j, 2);
 
       if (j == 0) {
         m = m_new;
@@ -316,41 +508,77 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
       const float m_safe = (m == -INFINITY) ? 0.f : m;
       const float neg_mc = -m_safe * c;
+      // P = exp2(s*c - m*c) in two 64-key halves; each half is written to TMEM and handed to the MMA thread as soon
+      // as it is complete, so the first half of P*V runs under the second half of the exps.
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
-        s[i] = ex2(fmaf(s[i], c, neg_mc));
-        s[i + 1] = ex2(fmaf(s[i + 1], c, neg_mc));
-        s[i + 2] = ex2(fmaf(s[i + 2], c, neg_mc));
-        s[i + 3] = ex2(fmaf(s[i + 3], c, neg_mc));
-        if constexpr (kTF32) {
-          // kind::tf32 reads only the top 19 bits of P; sum exactly those values so that O = (sum P~ V) / (sum P~)
-          // is normalised by what the tensor core actually multiplied (removes the truncation bias from O)
-          s[i] = __uint_as_float(__float_as_uint(s[i]) & 0xFFFFE000u);
-          s[i + 1] = __uint_as_float(__float_as_uint(s[i + 1]) & 0xFFFFE000u);
-          s[i + 2] = __uint_as_float(__float_as_uint(s[i + 2]) & 0xFFFFE000u);
-          s[i + 3] = __uint_as_float(__float_as_uint(s[i + 3]) & 0xFFFFE000u);
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int i = h * 64; i < h * 64 + 64; i += 4) {
+#if FA_OPT_F2
+          if constexpr (!kTF32) {
+          float2 a01 = ffma2(make_float2(s[i], s[i + 1]), make_float2(c, c), make_float2(neg_mc, neg_mc));
+          float2 a23 = ffma2(make_float2(s[i + 2], s[i + 3]), make_float2(c, c), make_float2(neg_mc, neg_mc));
+          s[i] = ex2(a01.x);
+          s[i + 1] = ex2(a01.y);
+          s[i + 2] = ex2(a23.x);
+          s[i + 3] = ex2(a23.y);
+          } else
+#endif
+          {
+          s[i] = ex2(fmaf(s[i], c, neg_mc));
+          s[i + 1] = ex2(fmaf(s[i + 1], c, neg_mc));
+          s[i + 2] = ex2(fmaf(s[i + 2], c, neg_mc));
+          s[i + 3] = ex2(fmaf(s[i + 3], c, neg_mc));
+          }
+          if constexpr (kTF32) {
+            // kind::tf32 reads only the top 19 bits of P; sum exactly those values so that O = (sum P~ V) / (sum P~)
+            // is normalised by what the tensor core actually multiplied (removes the truncation bias from O)
+            s[i] = __uint_as_float(__float_as_uint(s[i]) & 0xFFFFE000u);
+            s[i + 1] = __uint_as_float(__float_as_uint(s[i + 1]) & 0xFFFFE000u);
+            s[i + 2] = __uint_as_float(__float_as_uint(s[i + 2]) & 0xFFFFE000u);
+            s[i + 3] = __uint_as_float(__float_as_uint(s[i + 3]) & 0xFFFFE000u);
+          }
+#if FA_OPT_F2
+          if constexpr (!kTF32) {
+          const float2 s01 = fadd2(make_float2(l0, l1), make_float2(s[i], s[i + 1]));
+          const float2 s23 = fadd2(make_float2(l2, l3), make_float2(s[i + 2], s[i + 3]));
+          l0 = s01.x; l1 = s01.y; l2 = s23.x; l3 = s23.y;
+          } else
+#endif
+          {
+          l0 += s[i];
+          l1 += s[i + 1];
+          l2 += s[i + 2];
+          l3 += s[i + 3];
+          }
         }
-        l0 += s[i];
-        l1 += s[i + 1];
-        l2 += s[i + 2];
-        l3 += s[i + 3];
+        if constexpr (kTF32) {
+          tmem_st32(tS + h * 64, reinterpret_cast<uint32_t*>(&s[h * 64]));
+          tmem_st32(tS + h * 64 + 32, reinterpret_cast<uint32_t*>(&s[h * 64 + 32]));
+        } else {
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(s[h * 64 + 2 * i], s[h * 64 + 2 * i + 1]);
+          tmem_st32(tS + h * 32, &pk[0]);
+        }
+#if FA_OPT_SPLITP
+        if (tracer) FA_TRACE_AT(t, j, 3 + 2 * h);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_p + 16 * t + 8 * h);
+        if (tracer) FA_TRACE_AT(t, j, 4 + 2 * h);
+#else
+        if (h == 1) {
+          if (tracer) FA_TRACE_AT(t, j, 5);
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(bar_p + 16 * t + 8);
+          if (tracer) FA_TRACE_AT(t, j, 6);
+        }
+#endif
       }
       l += (l0 + l1) + (l2 + l3);
-
-      if constexpr (kTF32) {
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) tmem_st32(tS + q4 * 32, reinterpret_cast<uint32_t*>(&s[q4 * 32]));
-      } else {
-        uint32_t pk[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) pk[i] = pack_bf16x2(s[2 * i], s[2 * i + 1]);
-        tmem_st32(tS, &pk[0]);
-        tmem_st32(tS + 32, &pk[32]);
-      }
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(bar_p + 8 * t);
     }
 
     // ---- epilogue: O/l -> swizzled SMEM (reusing this tile's Q buffer) -> TMA store; LSE -> global ----

@@ -49,6 +49,7 @@ FA_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 FA_DEVINL void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag) {
+  if (mbar_try_wait(bar, parity)) return;  // fast path: already complete
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > FA_WATCHDOG_SPINS) {
@@ -207,10 +208,40 @@ FA_DEVINL void tmem_st16(uint32_t taddr, const uint32_t* r) {
 }
 
 // ------------------------------------------ misc ----------------------------------------------
+// exactly one lane of a fully converged warp gets `true` (the same lane every time)
+FA_DEVINL bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 FA_DEVINL float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 — two fp32 lanes per instruction)
+FA_DEVINL float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+FA_DEVINL float2 fadd2(float2 a, float2 b) {
+  uint64_t ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
 }
 FA_DEVINL uint32_t pack_bf16x2(float lo, float hi) {  // result: low 16 bits = bf16(lo), high = bf16(hi)
   uint32_t r;
