@@ -59,6 +59,12 @@ int probe_device(int* major_out) {
   return FA_OK;
 }
 
+int current_sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  return g_dev[dev].checked ? g_dev[dev].sms : 148;
+}
+
 // ---- cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -116,7 +122,7 @@ int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& m
     FA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kSmemBytes));
     attr_set = true;
   }
-  const int64_t grid = (int64_t)fp.num_m_blocks * fp.heads * fp.batch;
+  const int64_t grid = (int64_t)fp.n_big + 2 * ((int64_t)fp.num_m_blocks * fp.heads * fp.batch - fp.n_big);
   if (grid <= 0 || grid > 0x7fffffff) return FA_ERR_INVALID_ARG;
   kern<<<(unsigned)grid, fa::kNumThreads, T::kSmemBytes, st>>>(mq, mk, mv, mo, fp);
   FA_CUDA(cudaGetLastError());
@@ -167,6 +173,15 @@ int run_tc(const fa_params* p, cudaStream_t st) {
   fp.causal_offset = (int)(p->n_k - p->n_q);
   fp.num_m_blocks = (int)((p->n_q + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM));
   fp.lse = p->lse;
+  {
+    // whole waves of 256-row CTAs; a remainder of at most SMs/2 blocks runs as twice as many 128-row CTAs (one wave)
+    const int64_t nb = (int64_t)fp.num_m_blocks * fp.heads * fp.batch;
+    const int64_t sms = std::max(1, current_sm_count());
+    int64_t n_big = (nb / sms) * sms;
+    if (2 * (nb - n_big) > sms || getenv("FA_B200_NO_SPLIT_WAVE")) n_big = nb;
+    if (n_big > 0x3fffffff) return FA_ERR_INVALID_ARG;
+    fp.n_big = (int)n_big;
+  }
   fp.v_desc_hi = fa::make_sdesc_hi(v_lbo, v_sbo, v_layout);
   fp.trace = nullptr;
 #if FA_TRACE

@@ -70,6 +70,7 @@ struct FwdParams {
   float* lse;         // [batch, heads, n_q] or nullptr
   uint64_t v_desc_hi; // upper descriptor bits (LBO/SBO/layout) of V as the MN-major B operand of P*V
   unsigned long long* trace;  // FA_TRACE builds only; nullptr otherwise
+  int n_big;          // CTAs [0, n_big) own a 256-row block (tiles A+B); CTAs beyond own a 128-row half block (tile A only)
 };
 constexpr int kTraceSteps = 48;
 
@@ -127,13 +128,22 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const int lane = threadIdx.x & 31;
 
   // ---- work assignment: blockIdx.x -> (m block, head, batch); m fastest so neighbours share K/V in L2 ----
+  // Wave quantisation: the host sizes n_big to whole waves of 256-row blocks; the remainder blocks (if they are few
+  // enough) are issued as pairs of single-tile CTAs so the last, partial wave is half as long.
   int bid = blockIdx.x;
+  const bool single_tile = bid >= p.n_big;
+  int half = 0;
+  if (single_tile) {
+    const int k = bid - p.n_big;
+    half = k & 1;
+    bid = p.n_big + (k >> 1);
+  }
   int m_blk = bid % p.num_m_blocks;
   bid /= p.num_m_blocks;
   const int head = bid % p.heads;
   const int batch = bid / p.heads;
   if (kCausal) m_blk = p.num_m_blocks - 1 - m_blk;  // heaviest blocks first
-  const int row0 = m_blk * (2 * kBlockM);
+  const int row0 = m_blk * (2 * kBlockM) + half * kBlockM;
 
   // KV trip count per Q tile
   const int n_kv_total = (p.n_k + kBlockN - 1) / kBlockN;
@@ -146,7 +156,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const int last_key = r0 + kBlockM - 1 + p.causal_offset;
       n = last_key < 0 ? 0 : min(n_kv_total, last_key / kBlockN + 1);
     }
-    if (r0 >= p.n_q) n = 0;
+    if (r0 >= p.n_q || (single_tile && t == 1)) n = 0;
     n_tile[t] = n;
   }
   const int n_max = max(n_tile[0], n_tile[1]);

@@ -25,7 +25,7 @@ run bf16 128 8 8192 0 0 5 1
 cat $L
 if [ "$1" != "quick" ]; then
   echo "== pytest -m gpu" > gpurun_out/pytest.log
-  timeout 900 python -m pytest tests -x -q -m gpu >> gpurun_out/pytest.log 2>&1
+  timeout 900 python -m pytest tests -q -m gpu >> gpurun_out/pytest.log 2>&1
   tail -n 30 gpurun_out/pytest.log
   timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_ours.json 2>> gpurun_out/pytest.log
   cat gpurun_out/bench_ours.json

@@ -7,7 +7,7 @@ echo "== golden" > gpurun_out/round.log
 timeout 300 python tests/golden/make_golden.py >> gpurun_out/round.log 2>&1
 mkdir -p tests/golden && cp gpurun_out/golden/*.npz tests/golden/ 2>/dev/null
 echo "== pytest -m gpu" >> gpurun_out/round.log
-timeout 900 python -m pytest tests -x -q -m gpu >> gpurun_out/round.log 2>&1
+timeout 900 python -m pytest tests -q -m gpu >> gpurun_out/round.log 2>&1
 echo "== smoke" >> gpurun_out/round.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" >> gpurun_out/round.log 2>&1
 echo "== TMA tf32 conversion experiment" >> gpurun_out/round.log

@@ -1,0 +1,109 @@
+#!/usr/bin/env python
+"""Multi-GPU parity + timing (launch with torchrun, one process per GPU, NCCL):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        scripts/multi_gpu_check.py [--n-per-rank 16384] [--heads 32]
+
+  1. B x H sharding (configs 3/4): every rank runs its slice with no collective; the all-gathered result must equal the
+     unsharded single-GPU forward bit for bit.
+  2. Ring attention (config 5): sequence shards, NCCL send/recv K/V rotation overlapped with the local kernel, LSE merge;
+     checked against the single-GPU forward over the full sequence, non-causal and causal.
+  3. Timing of the C5-shaped ring (H=32, d=128, bf16, N = n_per_rank * P): max over ranks, CUDA events.
+Prints one JSON line per item on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import flashattention_c_b200 as fab  # noqa: E402
+from flashattention_c_b200.ring import gather_bh  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n-per-rank", type=int, default=16384)
+    ap.add_argument("--heads", type=int, default=32)
+    ap.add_argument("--reps", type=int, default=3)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    out = []
+
+    # ---- 1. B x H sharding parity (C4-like, reduced N) ----
+    g = torch.Generator(device="cpu").manual_seed(7)
+    B, H, N, d = 2, 8, 2048, 128
+    q, k, v = (torch.randn(B * H, N, d, generator=g).to(torch.bfloat16).to(dev) for _ in range(3))
+    o_loc = fab.sharded_attention(q, k, v, causal=True)
+    o_all = gather_bh(o_loc, B * H)
+    o_ref = fab.attention(q, k, v, causal=True)
+    out.append({"check": "bh_sharded_vs_single_gpu", "world": world, "bitwise_equal": bool(torch.equal(o_all, o_ref)),
+                "local_bh": int(o_loc.shape[0])})
+
+    # ---- 2. ring parity ----
+    for dtype, dd, tol in ((torch.bfloat16, 128, 2e-2), (torch.float32, 64, 2e-3)):
+        for causal in (False, True):
+            Hh, n_loc = 4, 1024
+            Nf = n_loc * world
+            gq = torch.Generator(device="cpu").manual_seed(11)
+            qf, kf, vf = (torch.randn(1, Hh, Nf, dd, generator=gq).to(dtype).to(dev) for _ in range(3))
+            sl = slice(rank * n_loc, (rank + 1) * n_loc)
+            o_r, lse_r = fab.ring_attention(qf[:, :, sl].contiguous(), kf[:, :, sl].contiguous(), vf[:, :, sl].contiguous(), causal=causal)
+            o_full, lse_full = fab.attention(qf, kf, vf, causal=causal, return_lse=True)
+            err = (o_r.float() - o_full[:, :, sl].float()).abs().max()
+            err_l = (lse_r - lse_full[:, :, sl]).abs().max()
+            t = torch.stack([err, err_l])
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out.append({"check": f"ring_vs_single_gpu dtype={str(dtype).split('.')[-1]} d={dd} causal={causal} N={Nf}", "world": world,
+                        "max_err_o": float(t[0]), "max_err_lse": float(t[1]), "ok": bool(t[0] < tol and t[1] < 2e-3)})
+
+    # ---- 3. C5-shaped ring timing ----
+    Hh, dd, n_loc = args.heads, 128, args.n_per_rank
+    gq = torch.Generator(device="cuda").manual_seed(100 + rank)
+    qs, ks, vs = (torch.randn(1, Hh, n_loc, dd, device=dev, generator=gq).to(torch.bfloat16) for _ in range(3))
+    fab.ring_attention(qs, ks, vs)  # warm-up (NCCL channels, kernels)
+    torch.cuda.synchronize()
+    dist.barrier()
+    times = []
+    for _ in range(args.reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        e0.record()
+        fab.ring_attention(qs, ks, vs)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    t = torch.tensor([min(times)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # local-only time for the same FLOPs (world steps against the resident shard, no transfers) = overlap reference
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(world):
+        fab.attention(qs, ks, vs, return_lse=True, out_f32=True)
+    e1.record()
+    torch.cuda.synchronize()
+    t_local = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+    n_total = n_loc * world
+    flops = 4.0 * Hh * n_total * n_total * dd
+    out.append({"check": f"ring_timing C5-shaped H={Hh} d={dd} bf16 N={n_total} ({n_loc}/GPU)", "world": world, "ms": round(float(t[0]), 3),
+                "tflops_total": round(flops / float(t[0]) * 1e-9, 1), "tflops_per_gpu": round(flops / float(t[0]) * 1e-9 / world, 1),
+                "ms_compute_only_same_flops": round(float(t_local[0]), 3),
+                "kv_bytes_sent_per_gpu_per_step": 2 * Hh * n_loc * dd * 2})
+    if rank == 0:
+        for o in out:
+            print(json.dumps(o), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
