@@ -38,6 +38,9 @@
 #define FA_OPT_F2 1       // packed FFMA2 / FADD2 for the scale-subtract and the row sum (bf16 instances only: in the tf32
                           // instances the per-element P truncation breaks register pairing and costs ~150 extra moves)
 #endif
+#ifndef FA_OPT_POLY
+#define FA_OPT_POLY 0     // of every 8 P elements, how many get exp2 from the FMA-pipe polynomial instead of MUFU.EX2 (0, 2, 4)
+#endif
 #ifndef FA_OPT_ISSUERS
 #define FA_OPT_ISSUERS 1  // MMA-issuer warps: 2 = one per Q tile (independent), 1 = one warp issuing A then B in order
 #endif
@@ -525,21 +528,46 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       for (int h = 0; h < 2; ++h) {
 #pragma unroll
         for (int i = h * 64; i < h * 64 + 64; i += 4) {
+          // which of these 4 elements take the polynomial route: the first FA_OPT_POLY/2 pairs of every 8 elements
+          const bool kPoly01 = (FA_OPT_POLY >= 2) && ((i & 4) == 0);
+          const bool kPoly23 = (FA_OPT_POLY >= 4) && ((i & 4) == 0);
 #if FA_OPT_F2
           if constexpr (!kTF32) {
           float2 a01 = ffma2(make_float2(s[i], s[i + 1]), make_float2(c, c), make_float2(neg_mc, neg_mc));
           float2 a23 = ffma2(make_float2(s[i + 2], s[i + 3]), make_float2(c, c), make_float2(neg_mc, neg_mc));
-          s[i] = ex2(a01.x);
-          s[i + 1] = ex2(a01.y);
-          s[i + 2] = ex2(a23.x);
-          s[i + 3] = ex2(a23.y);
+          if (kPoly01) {
+            a01 = exp2_poly2(a01);
+            s[i] = a01.x;
+            s[i + 1] = a01.y;
+          } else {
+            s[i] = ex2(a01.x);
+            s[i + 1] = ex2(a01.y);
+          }
+          if (kPoly23) {
+            a23 = exp2_poly2(a23);
+            s[i + 2] = a23.x;
+            s[i + 3] = a23.y;
+          } else {
+            s[i + 2] = ex2(a23.x);
+            s[i + 3] = ex2(a23.y);
+          }
           } else
 #endif
           {
-          s[i] = ex2(fmaf(s[i], c, neg_mc));
-          s[i + 1] = ex2(fmaf(s[i + 1], c, neg_mc));
-          s[i + 2] = ex2(fmaf(s[i + 2], c, neg_mc));
-          s[i + 3] = ex2(fmaf(s[i + 3], c, neg_mc));
+          if (kPoly01) {
+            s[i] = exp2_poly(fmaf(s[i], c, neg_mc));
+            s[i + 1] = exp2_poly(fmaf(s[i + 1], c, neg_mc));
+          } else {
+            s[i] = ex2(fmaf(s[i], c, neg_mc));
+            s[i + 1] = ex2(fmaf(s[i + 1], c, neg_mc));
+          }
+          if (kPoly23) {
+            s[i + 2] = exp2_poly(fmaf(s[i + 2], c, neg_mc));
+            s[i + 3] = exp2_poly(fmaf(s[i + 3], c, neg_mc));
+          } else {
+            s[i + 2] = ex2(fmaf(s[i + 2], c, neg_mc));
+            s[i + 3] = ex2(fmaf(s[i + 3], c, neg_mc));
+          }
           }
           if constexpr (kTF32) {
             // kind::tf32 reads only the top 19 bits of P; sum exactly those values so that O = (sum P~ V) / (sum P~)

@@ -243,6 +243,35 @@ FA_DEVINL float2 fadd2(float2 a, float2 b) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
   return d;
 }
+// exp2 on the FMA/ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax
+// polynomial (max relative error 7.5e-5, well under the bf16 / tf32 quantisation of P), 2^n by adding n to the
+// exponent field.  The magic constant 1.5 * 2^23 leaves round(x) in the low mantissa bits of (x + magic).
+constexpr float kExp2Magic = 12582912.0f;
+constexpr float kExp2C0 = 9.999280572e-01f, kExp2C1 = 6.932609677e-01f, kExp2C2 = 2.426111251e-01f, kExp2C3 = 5.517166853e-02f;
+FA_DEVINL float exp2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float xf = x + kExp2Magic;
+  const float n = xf - kExp2Magic;
+  const float f = x - n;
+  float p = fmaf(kExp2C3, f, kExp2C2);
+  p = fmaf(p, f, kExp2C1);
+  p = fmaf(p, f, kExp2C0);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
+}
+FA_DEVINL float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 xf = fadd2(x, make_float2(kExp2Magic, kExp2Magic));
+  const float2 n = fadd2(xf, make_float2(-kExp2Magic, -kExp2Magic));
+  const float2 f = ffma2(n, make_float2(-1.0f, -1.0f), x);
+  float2 p = ffma2(make_float2(kExp2C3, kExp2C3), f, make_float2(kExp2C2, kExp2C2));
+  p = ffma2(p, f, make_float2(kExp2C1, kExp2C1));
+  p = ffma2(p, f, make_float2(kExp2C0, kExp2C0));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(xf.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(xf.y) << 23));
+  return r;
+}
 FA_DEVINL uint32_t pack_bf16x2(float lo, float hi) {  // result: low 16 bits = bf16(lo), high = bf16(hi)
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
