@@ -293,3 +293,45 @@ def test_multi_gpu_sharding_and_ring_over_nccl(cuda_device):
     assert lines[0]["bitwise_equal"]
     ring = [l for l in lines if l["check"].startswith("ring_vs_single_gpu")]
     assert len(ring) == 4 and all(l["ok"] for l in ring), ring
+
+
+def test_cuda_graph_capture_and_replay(fab, cuda_device):
+    """The operator is asynchronous on the caller's stream and makes no host-side device calls besides the launch, so a
+    launch-bound sequence of small forwards can be captured once and replayed as a CUDA graph."""
+    q, k, v = (torch.randn(16, 1024, 64, device=cuda_device) for _ in range(3))
+    out = torch.empty_like(q)
+    fab.attention(q, k, v, causal=True, out=out)      # warm-up outside capture (module load, func attributes)
+    expect = out.clone()
+    out.zero_()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(4):
+                fab.attention(q, k, v, causal=True, out=out)
+    torch.cuda.current_stream().wait_stream(s)
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, expect)
+
+
+def test_back_to_back_launch_rate_small_shape(fab, cuda_device):
+    """C1-sized calls issued back to back must be GPU-bound, not host-bound (tensor maps are cached per thread)."""
+    import time
+
+    q, k, v = (torch.randn(2, 8, 1024, 64, device=cuda_device) for _ in range(3))
+    out = torch.empty_like(q)
+    for _ in range(10):
+        fab.attention(q, k, v, out=out)
+    torch.cuda.synchronize()
+    n = 200
+    t0 = time.perf_counter()
+    for _ in range(n):
+        fab.attention(q, k, v, out=out)
+    host_us = (time.perf_counter() - t0) / n * 1e6
+    torch.cuda.synchronize()
+    total_us = (time.perf_counter() - t0) / n * 1e6
+    print(f"C1 back-to-back: host {host_us:.1f} us/call, wall {total_us:.1f} us/call")
+    assert total_us < 60.0
