@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Reference CUDA kernel (oracle/_ref/flash_ref_d{32,64,128}.so = src/main.cpp + src/flashattention.cu rebuilt for sm_100a)
+vs this repo on every BASELINE shape, same B200, same run: kernel-only CUDA-event times (fp32 inputs for the reference;
+it has no bf16 path, so bf16 configs run on fp32 copies of the same values)."""
+import json
+import math
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import flashattention_c_b200 as fab  # noqa: E402
+from oracle import fa_oracle  # noqa: E402
+
+SHAPES = [("C1", 16, 1024, 64, torch.float32), ("C2", 16, 8192, 64, torch.float32), ("C3", 128, 1024, 32, torch.float32),
+          ("C4", 128, 8192, 128, torch.bfloat16), ("C5 (one GPU, full N)", 32, 131072, 128, torch.bfloat16)]
+
+
+def timeit(fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return min(ts)
+
+
+for name, bh, n, d, dt in SHAPES:
+    big = n > 10000
+    g = torch.Generator(device="cuda").manual_seed(1)
+    q, k, v = (torch.randn(bh, n, d, device="cuda", generator=g) for _ in range(3))
+    ext = fa_oracle.load_ref_torch_ext(d)
+    t_ref = timeit(lambda: ext.forward(q, k, v, False), 1 if big else 3)
+    o_ref = ext.forward(q, k, v, False)
+    qq, kk, vv = (x.to(dt) for x in (q, k, v))
+    t_ours = timeit(lambda: fab.attention(qq, kk, vv, scale=1.0), 3 if big else 10)
+    o = fab.attention(qq, kk, vv, scale=1.0).float()
+    fl = 4.0 * bh * n * n * d
+    print(json.dumps({"config": name, "bh": bh, "n": n, "d": d, "dtype": str(dt).split(".")[-1], "ref_ms": round(t_ref, 3),
+                      "ref_tflops": round(fl / t_ref * 1e-9, 2), "ours_ms": round(t_ours, 4), "ours_tflops": round(fl / t_ours * 1e-9, 1),
+                      "speedup": round(t_ref / t_ours, 1), "max_abs_diff_vs_reference_kernel_scale1": float((o - o_ref).abs().max())}), flush=True)
+    del q, k, v, qq, kk, vv, o, o_ref
