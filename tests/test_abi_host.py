@@ -100,3 +100,29 @@ def test_ring_schedule_visits_every_shard_once():
         for s in range(1, world):
             for r in range(world):
                 assert ring_schedule(r, world)[s][1] == ring_schedule((r - 1) % world, world)[s - 1][1]
+
+
+def test_bench_reference_arm_prints_contract_line_without_gpu():
+    """`bench.py --impl reference` must always print one JSON line with the contract keys; on a GPU-less box it times
+    the oracle's CPU port on a bounded sample (the CUDA reference arm is exercised on the B200)."""
+    import json
+    import sys
+
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only behaviour")
+    res = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-1000:]
+    line = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "higher_is_better", "impl", "cpu_baseline", "e2e", "config"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_own_arm_refuses_to_run_without_gpu():
+    import sys
+
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only behaviour")
+    res = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
+    assert res.returncode != 0 and "no CPU fallback" in (res.stderr + res.stdout)
