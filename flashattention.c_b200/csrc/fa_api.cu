@@ -207,6 +207,9 @@ int run_tc(const fa_params* p, cudaStream_t st) {
     if (2 * (nb - n_big) > sms || getenv("FA_B200_NO_SPLIT_WAVE")) n_big = nb;
     if (n_big > 0x3fffffff) return FA_ERR_INVALID_ARG;
     fp.n_big = (int)n_big;
+    // the remainder CTAs split their K/V range over the two tile slots (FA_B200_TAIL_SPLIT=0: one slot, A/B aid)
+    const char* ts = getenv("FA_B200_TAIL_SPLIT");   // read per call so a test can compare both modes in one process
+    fp.tail_split = (ts && atoi(ts) == 0) ? 0 : 1;
   }
   fp.v_desc_hi = fa::make_sdesc_hi(v_lbo, v_sbo, v_layout);
   fp.trace = nullptr;

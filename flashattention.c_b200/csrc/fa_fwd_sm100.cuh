@@ -12,12 +12,19 @@
 // tensor pipe: while the softmax warps of one tile work on S_j, the MMA thread runs P*V and the next
 // Q*K^T of the other tile.
 //
-// Warp roles (352 threads): warps 0-3 softmax/epilogue of tile A, 4-7 of tile B (warp w reads TMEM lanes
-// 32*(w%4)..+31), warp 8 lane 0 = TMA producer (+ TMEM alloc/dealloc by the whole warp), warps 9 and 10 = MMA
-// issuers of tile A and tile B (one elected lane each).  One issuer per tile matters: `tcgen05.mma` issue
-// back-pressures at the rate the tensor pipe retires (~64 cycles per 128x128x16 MMA) and every mbarrier
-// wait + tcgen05 fence costs ~200 cycles even when already complete, so with a single issuer thread all of its
-// waiting shows up as tensor-pipe idle time (measured: profiles/r01_trace_v1_c4_report.txt).
+// Warp roles (320 threads): warps 0-3 softmax/epilogue of tile A, 4-7 of tile B (warp w reads TMEM lanes
+// 32*(w%4)..+31), warp 8 lane 0 = TMA producer (+ TMEM alloc/dealloc by the whole warp), warp 9 = MMA issuer
+// (converged warp, one elected lane issues A then B in order).  `tcgen05.mma` issue back-pressures at the rate the
+// tensor pipe retires (~64 cycles per 128x128x16 MMA) and every mbarrier wait + tcgen05 fence costs ~200 cycles
+// even when already complete (measured: profiles/r01_trace_v1_c4_report.txt), so waits are batched.  Two
+// independent issuer warps (one per tile) were measured and rejected: the tiles fall into lock-step
+// (profiles/r01_ab_issuer_modes_session9.log).
+//
+// Tail CTAs.  The host sizes the grid as whole waves of 256-row CTAs plus a remainder wave of 128-row CTAs.  A
+// remainder CTA runs its one Q tile in "split-KV" mode: tile slot A attends the first half of the K/V tiles and
+// slot B the second half (same Q rows), so the two halves ping-pong on the tensor pipe exactly like two Q tiles
+// do, and the partial (O, m, l) pairs are merged by the log-sum-exp rule through SMEM in the epilogue.  The serial
+// chain of a tail CTA is therefore half as long (C1 is nothing but tail CTAs).
 //
 // TMEM columns (512 allocated): S_A [0,128)  S_B [128,256)  O_A [256,256+d)  O_B [256+d, 256+2d).
 // P aliases S: bf16 path packs two bf16 per column into S cols [0,64); tf32 path overwrites S in place.
@@ -40,12 +47,6 @@
 #endif
 #ifndef FA_OPT_POLY
 #define FA_OPT_POLY 0     // of every 8 P elements, how many get exp2 from the FMA-pipe polynomial instead of MUFU.EX2 (0, 2, 4)
-#endif
-#ifndef FA_OPT_ISSUERS
-#define FA_OPT_ISSUERS 1  // MMA-issuer warps: 2 = one per Q tile (independent), 1 = one warp issuing A then B in order
-#endif
-#ifndef FA_OPT_STAGGER
-#define FA_OPT_STAGGER 0  // (2 issuers) start tile B half a step late so the two tiles run in anti-phase
 #endif
 // -DFA_TRACE=1 builds a timeline-tracing kernel: CTA 0 records clock64() at every pipeline hand-off of its first
 // kTraceSteps KV tiles into FwdParams::trace ([role 0..3][step][slot 0..7]); see scripts/trace_report.py.
@@ -73,14 +74,17 @@ struct FwdParams {
   float* lse;         // [batch, heads, n_q] or nullptr
   uint64_t v_desc_hi; // upper descriptor bits (LBO/SBO/layout) of V as the MN-major B operand of P*V
   unsigned long long* trace;  // FA_TRACE builds only; nullptr otherwise
-  int n_big;          // CTAs [0, n_big) own a 256-row block (tiles A+B); CTAs beyond own a 128-row half block (tile A only)
+  int n_big;          // CTAs [0, n_big) own a 256-row block (tiles A+B); CTAs beyond own a 128-row half block
+  int tail_split;     // != 0: a 128-row CTA splits its K/V range over tile slots A and B (merged in the epilogue);
+                      // 0: it runs slot A only
 };
 constexpr int kTraceSteps = 48;
 
 constexpr int kBlockM = 128;          // rows per Q tile
 constexpr int kBlockN = 128;          // keys per K/V tile
 constexpr int kChunkBytes = 128 * 128;  // one TMA box: 128 rows x 128 bytes
-constexpr int kNumThreads = 352;      // 8 softmax warps + TMA producer + one MMA-issuer warp per Q tile
+constexpr int kNumThreads = 320;      // 8 softmax warps + TMA producer warp + MMA-issuer warp
+constexpr int kBarMerge = 3;          // named barrier: slot B hands its partial (O, m, l) to slot A (split-KV tail CTAs)
 constexpr float kRescaleThreshold = 8.0f;  // lazy rescale: keep a stale max while it is within 2^8
 
 template <bool kTF32, int kHeadDim, bool kOutF32>
@@ -132,7 +136,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
   // ---- work assignment: blockIdx.x -> (m block, head, batch); m fastest so neighbours share K/V in L2 ----
   // Wave quantisation: the host sizes n_big to whole waves of 256-row blocks; the remainder blocks (if they are few
-  // enough) are issued as pairs of single-tile CTAs so the last, partial wave is half as long.
+  // enough) are issued as pairs of 128-row CTAs so the last, partial wave is short.
   int bid = blockIdx.x;
   const bool single_tile = bid >= p.n_big;
   int half = 0;
@@ -147,10 +151,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const int batch = bid / p.heads;
   if (kCausal) m_blk = p.num_m_blocks - 1 - m_blk;  // heaviest blocks first
   const int row0 = m_blk * (2 * kBlockM) + half * kBlockM;
+  const bool split = single_tile && p.tail_split != 0;   // slots A and B = two halves of the K/V range of ONE Q tile
 
-  // KV trip count per Q tile
+  // KV trip count and first K/V tile of each tile slot
   const int n_kv_total = (p.n_k + kBlockN - 1) / kBlockN;
   int n_tile[2];
+  int kv_first[2] = {0, 0};
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     const int r0 = row0 + t * kBlockM;
@@ -162,16 +168,22 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     if (r0 >= p.n_q || (single_tile && t == 1)) n = 0;
     n_tile[t] = n;
   }
+  if (split) {
+    const int n = n_tile[0];
+    n_tile[0] = (n + 1) >> 1;
+    n_tile[1] = n - n_tile[0];
+    kv_first[1] = n_tile[0];
+  }
   const int n_max = max(n_tile[0], n_tile[1]);
+  const int row_of_tile1 = split ? row0 : row0 + kBlockM;   // first Q row of slot B
 
   // ---- one-time setup ----
   if (warp == 9 && lane == 0) {
     mbar_init(bar_q, 1);
     mbar_init(bar_q + 8, 1);
-    const uint32_t n_active = (n_tile[0] > 0 ? 1u : 0u) + (n_tile[1] > 0 ? 1u : 0u);
     for (int i = 0; i < T::kNBuf; ++i) {
       mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, (FA_OPT_ISSUERS == 2 && n_active > 0) ? n_active : 1u);   // every issuer releases the slot
+      mbar_init(bar_empty + 8 * i, 1);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar_s + 8 * t, 1);
@@ -200,9 +212,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (warp == 8) {
     // =========================== TMA producer ===========================
     if (lane == 0 && n_max > 0) {
+      // Q: one tile per slot; in split mode both slots read the same Q tile from buffer 0
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        if (n_tile[t] > 0) {
+        if (n_tile[t] > 0 && !(split && t == 1)) {
           mbar_arrive_expect_tx(bar_q + 8 * t, T::kTileBytes);
 #pragma unroll
           for (int c = 0; c < T::kDChunks; ++c)
@@ -210,27 +223,42 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                         row0 + t * kBlockM, head, batch);
         }
       }
-      const int n_loads = 2 * n_max;  // K_0, V_0, K_1, V_1, ...
-      for (int i = 0; i < n_loads; ++i) {
-        const int buf = i % T::kNBuf;
-        const int round = i / T::kNBuf;
+      int ring = 0;   // running index into the K/V ring; the MMA issuer consumes tiles in exactly this order
+      auto load = [&](const CUtensorMap* tm, int kv_tile) {
+        const int buf = ring % T::kNBuf;
+        const int round = ring / T::kNBuf;
+        ++ring;
         if (round > 0) mbar_wait(bar_empty + 8 * buf, (round - 1) & 1, TAG_KV_EMPTY);
         mbar_arrive_expect_tx(bar_full + 8 * buf, T::kTileBytes);
-        const CUtensorMap* tm = (i & 1) ? &tm_v : &tm_k;
-        const int kv0 = (i >> 1) * kBlockN;
 #pragma unroll
         for (int c = 0; c < T::kDChunks; ++c)
-          tma_load_4d(sKV + buf * T::kTileBytes + c * kChunkBytes, tm, bar_full + 8 * buf, c * T::kElemsPerChunk, kv0,
-                      head, batch);
+          tma_load_4d(sKV + buf * T::kTileBytes + c * kChunkBytes, tm, bar_full + 8 * buf, c * T::kElemsPerChunk,
+                      kv_tile * kBlockN, head, batch);
+      };
+      if (!split) {
+        for (int j = 0; j < n_max; ++j) {   // K_0, V_0, K_1, V_1, ... shared by both Q tiles
+          load(&tm_k, j);
+          load(&tm_v, j);
+        }
+      } else {
+        // K_A0, K_B0, then per step: V_A(j), K_A(j+1), V_B(j), K_B(j+1)
+        const int nA = n_tile[0], nB = n_tile[1];
+        load(&tm_k, 0);
+        if (nB > 0) load(&tm_k, nA);
+        for (int j = 0; j < nA; ++j) {
+          load(&tm_v, j);
+          if (j + 1 < nA) load(&tm_k, j + 1);
+          if (j < nB) {
+            load(&tm_v, nA + j);
+            if (j + 1 < nB) load(&tm_k, nA + j + 1);
+          }
+        }
       }
     }
-  } else if (warp == 9 || warp == 10) {
-    // =========================== MMA issuer(s) ===========================
-    // The whole warp follows the control flow (so every branch is warp-uniform); one elected lane issues.
-#if FA_OPT_ISSUERS == 2
-    const int t = warp - 9;
-    const int n_mine = n_tile[t];
-    if (n_mine > 0) {
+  } else if (warp == 9) {
+    // =========================== MMA issuer ===========================
+    // The whole warp follows the (warp-uniform) control flow and waits on the mbarriers; one elected lane issues.
+    if (n_max > 0) {
       constexpr uint32_t kFmt = kTF32 ? 2u : 1u;
       constexpr uint32_t idesc_s = make_idesc(kFmt, 0, kBlockM, kBlockN);
       constexpr uint32_t idesc_pv = make_idesc(kFmt, 1, kBlockM, kHeadDim);
@@ -243,119 +271,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const uint64_t hi_mnmajor = p.v_desc_hi;
       constexpr int kKStepsS = kHeadDim / T::kUmmaK;   // k-steps of Q K^T (32 bytes each)
       constexpr int kKStepsPV = kBlockN / T::kUmmaK;   // k-steps of P V (UmmaK keys each)
-      const uint32_t tmem_s = tmem_base + T::kTmemS + t * kBlockN;   // S_t, and P_t which aliases it
-      const uint32_t tmem_o = tmem_base + T::kTmemO + t * kHeadDim;
-      const uint64_t qd = sdesc_at(hi_kmajor, sQ + t * T::kTileBytes);
-
       // Descriptors are built once per operand tile; a k-step only adds to the 14-bit start-address field
       // ((bytes >> 4); SMEM addresses are < 2^18, so the field never carries).
-      auto issue_s = [&](int buf) {
-        const uint64_t kd = sdesc_at(hi_kmajor, sKV + buf * T::kTileBytes);
-#pragma unroll
-        for (int kk = 0; kk < kKStepsS; ++kk) {
-          const uint32_t off16 = ((kk >> 2) * kChunkBytes + (kk & 3) * 32) >> 4;
-          mma_ss<kTF32>(tmem_s, qd + off16, kd + off16, idesc_s, kk > 0 ? 1u : 0u);
-        }
-      };
-      // P*V for k-steps [ks0, ks1) of the 128-key tile
-      auto issue_pv = [&](int buf, bool accumulate, int ks0, int ks1) {
-        const uint64_t vd = sdesc_at(hi_mnmajor, sKV + buf * T::kTileBytes);
-#pragma unroll
-        for (int ks = ks0; ks < ks1; ++ks) {
-          mma_ts<kTF32>(tmem_o, tmem_s + ks * 8, vd + static_cast<uint32_t>(ks * (T::kUmmaK * 128 / 16)), idesc_pv,
-                        (accumulate || ks > 0) ? 1u : 0u);
-        }
-      };
-
-      mbar_wait(bar_q + 8 * t, 0, TAG_Q_FULL);
-#if FA_OPT_STAGGER
-      // anti-phase start: tile B's first S is issued only when tile A's softmax is half-way through its first tile
-      if (t == 1 && n_tile[0] > 1) mbar_wait(bar_p + (FA_OPT_SPLITP ? 0 : 8), 0, TAG_P_FULL);
-#endif
-      // prologue: S_t(0) = Q_t K_0^T
-      mbar_wait(bar_full + 0, 0, TAG_KV_FULL);
-      tc_fence_after();
-      if (elect_one_sync()) {
-        issue_s(0);
-        tc_commit(bar_s + 8 * t);
-        tc_commit(bar_empty + 0);
-      }
-      __syncwarp();
-
-      for (int j = 0; j < n_mine; ++j) {
-        const int iv = 2 * j + 1;   // ring index of V_j
-        const int ik = 2 * j + 2;   // ring index of K_{j+1}
-        const int vbuf = iv % T::kNBuf;
-        const int kbuf = ik % T::kNBuf;
-        const bool last = (j == n_mine - 1);
-        mbar_wait(bar_full + 8 * vbuf, (iv / T::kNBuf) & 1, TAG_KV_FULL);
-        tc_fence_after();
-#if FA_OPT_SPLITP
-        FA_TRACE_AT(2 + t, j, 0);
-        mbar_wait(bar_p + 16 * t, j & 1, TAG_P_FULL);          // keys [0, 64) of P are in TMEM
-        tc_fence_after();
-        FA_TRACE_AT(2 + t, j, 1);
-        if (elect_one_sync()) issue_pv(vbuf, j > 0, 0, kKStepsPV / 2);
-        __syncwarp();
-        FA_TRACE_AT(2 + t, j, 2);
-        mbar_wait(bar_p + 16 * t + 8, j & 1, TAG_P_FULL);      // keys [64, 128)
-        tc_fence_after();
-        FA_TRACE_AT(2 + t, j, 3);
-        if (elect_one_sync()) {
-          issue_pv(vbuf, j > 0, kKStepsPV / 2, kKStepsPV);
-          if (last) tc_commit(bar_o + 8 * t);
-          tc_commit(bar_empty + 8 * vbuf);
-        }
-        __syncwarp();
-        FA_TRACE_AT(2 + t, j, 4);
-#else
-        FA_TRACE_AT(2 + t, j, 0);
-        mbar_wait(bar_p + 16 * t + 8, j & 1, TAG_P_FULL);
-        tc_fence_after();
-        FA_TRACE_AT(2 + t, j, 3);
-        if (elect_one_sync()) {
-          issue_pv(vbuf, j > 0, 0, kKStepsPV);
-          if (last) tc_commit(bar_o + 8 * t);
-          tc_commit(bar_empty + 8 * vbuf);
-        }
-        __syncwarp();
-        FA_TRACE_AT(2 + t, j, 4);
-#endif
-        if (!last) {
-          mbar_wait(bar_full + 8 * kbuf, (ik / T::kNBuf) & 1, TAG_KV_FULL);
-          tc_fence_after();
-          FA_TRACE_AT(2 + t, j, 5);
-          if (elect_one_sync()) {
-            issue_s(kbuf);
-            tc_commit(bar_s + 8 * t);
-            tc_commit(bar_empty + 8 * kbuf);
-          }
-          __syncwarp();
-          FA_TRACE_AT(2 + t, j, 6);
-        }
-      }
-      // K/V tiles this Q tile does not need (causal: the other tile reaches one tile further) still need this
-      // issuer's release; follow the ring in order (wait full, then arrive) so a slot is never released early.
-      if (lane == 0) {
-        for (int i = 2 * n_mine; i < 2 * n_max; ++i) {
-          const int buf = i % T::kNBuf;
-          mbar_wait(bar_full + 8 * buf, (i / T::kNBuf) & 1, TAG_KV_FULL);
-          mbar_arrive(bar_empty + 8 * buf);
-        }
-      }
-      __syncwarp();
-    }
-#else   // ---------------- FA_OPT_ISSUERS == 1: warp 9 issues for both tiles, A then B, in order ----------------
-    if (warp == 9 && n_max > 0) {
-      constexpr uint32_t kFmt = kTF32 ? 2u : 1u;
-      constexpr uint32_t idesc_s = make_idesc(kFmt, 0, kBlockM, kBlockN);
-      constexpr uint32_t idesc_pv = make_idesc(kFmt, 1, kBlockM, kHeadDim);
-      constexpr uint64_t hi_kmajor = make_sdesc_hi_sw128(16, 1024);
-      const uint64_t hi_mnmajor = p.v_desc_hi;
-      constexpr int kKStepsS = kHeadDim / T::kUmmaK;
-      constexpr int kKStepsPV = kBlockN / T::kUmmaK;
-      auto issue_s = [&](int t, int buf) {
-        const uint64_t qd = sdesc_at(hi_kmajor, sQ + t * T::kTileBytes);
+      auto issue_s = [&](int t, int qbuf, int buf) {
+        const uint64_t qd = sdesc_at(hi_kmajor, sQ + qbuf * T::kTileBytes);
         const uint64_t kd = sdesc_at(hi_kmajor, sKV + buf * T::kTileBytes);
         const uint32_t d = tmem_base + T::kTmemS + t * kBlockN;
 #pragma unroll
@@ -364,6 +283,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           mma_ss<kTF32>(d, qd + off16, kd + off16, idesc_s, kk > 0 ? 1u : 0u);
         }
       };
+      // P*V for k-steps [ks0, ks1) of the 128-key tile; A = P_t read from TMEM (it aliases S_t)
       auto issue_pv = [&](int t, int buf, bool accumulate, int ks0, int ks1) {
         const uint64_t vd = sdesc_at(hi_mnmajor, sKV + buf * T::kTileBytes);
         const uint32_t d = tmem_base + T::kTmemO + t * kHeadDim;
@@ -374,68 +294,108 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                         (accumulate || ks > 0) ? 1u : 0u);
         }
       };
-      if (n_tile[0] > 0) mbar_wait(bar_q, 0, TAG_Q_FULL);
-      if (n_tile[1] > 0) mbar_wait(bar_q + 8, 0, TAG_Q_FULL);
-      mbar_wait(bar_full + 0, 0, TAG_KV_FULL);
-      tc_fence_after();
-      if (elect_one_sync()) {
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (n_tile[t] > 0) {
-            issue_s(t, 0);
-            tc_commit(bar_s + 8 * t);
-          }
-        }
-        tc_commit(bar_empty + 0);
-      }
-      __syncwarp();
-      for (int j = 0; j < n_max; ++j) {
-        const int iv = 2 * j + 1, ik = 2 * j + 2;
-        const int vbuf = iv % T::kNBuf, kbuf = ik % T::kNBuf;
-        mbar_wait(bar_full + 8 * vbuf, (iv / T::kNBuf) & 1, TAG_KV_FULL);
-        if (j + 1 < n_max) mbar_wait(bar_full + 8 * kbuf, (ik / T::kNBuf) & 1, TAG_KV_FULL);
-        tc_fence_after();
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (j < n_tile[t]) {
-            const bool last = (j == n_tile[t] - 1);
+      auto wait_full = [&](int i) { mbar_wait(bar_full + 8 * (i % T::kNBuf), (i / T::kNBuf) & 1, TAG_KV_FULL); };
+      // P_t(j) V -> O_t in two 64-key halves as the softmax warps deliver them, then (unless this was the slot's last
+      // K/V tile) S_t(j+1); the tensor pipe executes in issue order, so S_t(j+1) may overwrite the columns P_t(j) aliased.
+      auto step = [&](int t, int j, bool last, int qbuf, int vbuf, int kbuf, bool release) {
 #if FA_OPT_SPLITP
-            FA_TRACE_AT(2 + t, j, 0);
-            mbar_wait(bar_p + 16 * t, j & 1, TAG_P_FULL);
-            tc_fence_after();
-            FA_TRACE_AT(2 + t, j, 1);
-            if (elect_one_sync()) issue_pv(t, vbuf, j > 0, 0, kKStepsPV / 2);
-            __syncwarp();
-            FA_TRACE_AT(2 + t, j, 2);
+        FA_TRACE_AT(2 + t, j, 0);
+        mbar_wait(bar_p + 16 * t, j & 1, TAG_P_FULL);          // keys [0, 64) of P are in TMEM
+        tc_fence_after();
+        FA_TRACE_AT(2 + t, j, 1);
+        if (elect_one_sync()) issue_pv(t, vbuf, j > 0, 0, kKStepsPV / 2);
+        __syncwarp();
+        FA_TRACE_AT(2 + t, j, 2);
 #endif
-            mbar_wait(bar_p + 16 * t + 8, j & 1, TAG_P_FULL);
-            tc_fence_after();
-            FA_TRACE_AT(2 + t, j, 3);
-            if (elect_one_sync()) {
-              issue_pv(t, vbuf, j > 0, FA_OPT_SPLITP ? kKStepsPV / 2 : 0, kKStepsPV);
-              if (last) tc_commit(bar_o + 8 * t);
-              if (!last) {
-                issue_s(t, kbuf);
-                tc_commit(bar_s + 8 * t);
-              }
-            }
-            __syncwarp();
-            FA_TRACE_AT(2 + t, j, 6);
-          }
-        }
+        mbar_wait(bar_p + 16 * t + 8, j & 1, TAG_P_FULL);      // keys [64, 128)
+        tc_fence_after();
+        FA_TRACE_AT(2 + t, j, 3);
         if (elect_one_sync()) {
-          tc_commit(bar_empty + 8 * vbuf);
-          if (j + 1 < n_max) tc_commit(bar_empty + 8 * kbuf);
+          issue_pv(t, vbuf, j > 0, FA_OPT_SPLITP ? kKStepsPV / 2 : 0, kKStepsPV);
+          if (release) tc_commit(bar_empty + 8 * vbuf);
+          if (last) {
+            tc_commit(bar_o + 8 * t);
+          } else {
+            issue_s(t, qbuf, kbuf);
+            tc_commit(bar_s + 8 * t);
+            if (release) tc_commit(bar_empty + 8 * kbuf);
+          }
         }
         __syncwarp();
+        FA_TRACE_AT(2 + t, j, 6);
+      };
+
+      if (!split) {
+        // ---- two Q tiles share every K/V tile: ring index of K_j is 2j, of V_j is 2j+1 ----
+        if (n_tile[0] > 0) mbar_wait(bar_q, 0, TAG_Q_FULL);
+        if (n_tile[1] > 0) mbar_wait(bar_q + 8, 0, TAG_Q_FULL);
+        wait_full(0);
+        tc_fence_after();
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (n_tile[t] > 0) {
+              issue_s(t, t, 0);
+              tc_commit(bar_s + 8 * t);
+            }
+          }
+          tc_commit(bar_empty + 0);
+        }
+        __syncwarp();
+        for (int j = 0; j < n_max; ++j) {
+          const int iv = 2 * j + 1, ik = 2 * j + 2;
+          const int vbuf = iv % T::kNBuf, kbuf = ik % T::kNBuf;
+          wait_full(iv);
+          if (j + 1 < n_max) wait_full(ik);
+          tc_fence_after();
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+            if (j < n_tile[t]) step(t, j, j == n_tile[t] - 1, t, vbuf, kbuf, false);
+          if (elect_one_sync()) {
+            tc_commit(bar_empty + 8 * vbuf);
+            if (j + 1 < n_max) tc_commit(bar_empty + 8 * kbuf);
+          }
+          __syncwarp();
+        }
+      } else {
+        // ---- split-KV: each slot has its own K/V tiles; ring order K_A0, K_B0, then V_A(j), K_A(j+1), V_B(j), K_B(j+1) ----
+        mbar_wait(bar_q, 0, TAG_Q_FULL);
+        wait_full(0);
+        if (n_tile[1] > 0) wait_full(1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          issue_s(0, 0, 0);
+          tc_commit(bar_s);
+          tc_commit(bar_empty);
+          if (n_tile[1] > 0) {
+            issue_s(1, 0, 1);
+            tc_commit(bar_s + 8);
+            tc_commit(bar_empty + 8);
+          }
+        }
+        __syncwarp();
+        int ring = n_tile[1] > 0 ? 2 : 1;
+        for (int j = 0; j < n_max; ++j) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (j < n_tile[t]) {
+              const bool last = (j == n_tile[t] - 1);
+              const int iv = ring++;
+              const int ik = last ? iv : ring++;
+              wait_full(iv);
+              if (!last) wait_full(ik);
+              tc_fence_after();
+              step(t, j, last, 0, iv % T::kNBuf, ik % T::kNBuf, true);
+            }
+          }
+        }
       }
     }
-#endif
   } else {
     // =========================== softmax + epilogue (warps 0-7) ===========================
-    const int t = warp >> 2;                       // Q tile of this warpgroup
+    const int t = warp >> 2;                       // tile slot of this warpgroup
     const int r = (warp & 3) * 32 + lane;          // row within the tile == TMEM lane
-    const int q_row = row0 + t * kBlockM + r;
+    const int q_row = (t == 0 ? row0 : row_of_tile1) + r;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t tS = tmem_base + lane_base + T::kTmemS + t * kBlockN;
     const uint32_t tO = tmem_base + lane_base + T::kTmemO + t * kHeadDim;
@@ -454,7 +414,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (tracer) FA_TRACE_AT(t, j, 1);
       float s[128];
       // masking: key kv0 + i is visible iff i <= limit
-      const int kv0 = j * kBlockN;
+      const int kv0 = (kv_first[t] + j) * kBlockN;
       int limit = p.n_k - 1 - kv0;
       if (kCausal) limit = min(limit, q_row + p.causal_offset - kv0);
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
@@ -624,17 +584,58 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_wait(bar_o + 8 * t, 0, TAG_O_FINAL);
       tc_fence_after();
     }
-    const float inv_l = (n_mine > 0 && l > 0.f) ? 1.0f / l : 0.f;
-    if (p.lse != nullptr && q_row < p.n_q) {
+    // scale of this slot's accumulator and of the partner's partial (split-KV tail CTAs only) in the final O
+    float f_self = (n_mine > 0 && l > 0.f) ? 1.0f / l : 0.f;
+    float f_other = 0.f;
+    float lse_val = -INFINITY;
+    {
       const float m_safe = (m == -INFINITY) ? 0.f : m;
-      const float lse = (n_mine > 0 && l > 0.f) ? m_safe * p.scale + logf(l) : -INFINITY;
-      p.lse[(static_cast<int64_t>(batch) * p.heads + head) * p.n_q + q_row] = lse;
+      if (n_mine > 0 && l > 0.f) lse_val = m_safe * p.scale + logf(l);
     }
+    // split-KV exchange area: the K/V ring is dead once both slots' last MMAs have retired.
+    // xO[col][row] fp32 (column-major: a warp's 32 rows are 32 consecutive words -> conflict-free), then m[128], l[128]
+    const uint32_t xO = sKV;
+    const uint32_t xML = sKV + kHeadDim * kBlockM * 4;
+    bool stores = !(single_tile && t == 1);        // slot B of a 128-row CTA owns no output rows
+    // both accumulators final => every tcgen05.mma that read the ring has retired
+    if (split && n_tile[t ^ 1] > 0) mbar_wait(bar_o + 8 * (t ^ 1), 0, TAG_O_FINAL);
+    if (split && n_tile[1] > 0) {
+      tc_fence_after();
+      if (t == 1) {
+#pragma unroll
+        for (int cc = 0; cc < kHeadDim / 32; ++cc) {
+          uint32_t o[32];
+          tmem_ld32(tO + cc * 32, o);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) st_shared_b32(xO + ((cc * 32 + i) * kBlockM + r) * 4, o[i]);
+        }
+        st_shared_b32(xML + r * 4, __float_as_uint(m));
+        st_shared_b32(xML + (kBlockM + r) * 4, __float_as_uint(l));
+        named_bar_arrive(kBarMerge, 256);
+      } else {
+        named_bar_sync(kBarMerge, 256);
+        const float m_b = __uint_as_float(ld_shared_b32(xML + r * 4));
+        const float l_b = __uint_as_float(ld_shared_b32(xML + (kBlockM + r) * 4));
+        // log-sum-exp merge of (O_A, m, l) and (O_B, m_b, l_b); both maxima are in raw q.k units, sums in the exp2 domain
+        const float m_all = fmaxf(m, m_b);
+        const float a_a = (m == -INFINITY) ? 0.f : ex2((m - m_all) * c);
+        const float a_b = (m_b == -INFINITY) ? 0.f : ex2((m_b - m_all) * c);
+        const float l_all = l * a_a + l_b * a_b;
+        const float inv = l_all > 0.f ? 1.0f / l_all : 0.f;
+        f_self = a_a * inv;
+        f_other = a_b * inv;
+        lse_val = l_all > 0.f ? m_all * p.scale + logf(l_all) : -INFINITY;
+      }
+    }
+    if (p.lse != nullptr && stores && q_row < p.n_q)
+      p.lse[(static_cast<int64_t>(batch) * p.heads + head) * p.n_q + q_row] = lse_val;
     const uint32_t stage = sQ + t * T::kTileBytes;       // kDChunks boxes of 16 KB
     const uint32_t row_off = r * 128;
     const uint32_t sw = r & 7;
     constexpr int kRounds = T::kOChunks / T::kDChunks;   // 1, or 2 for bf16-in / fp32-out
     constexpr int kColsPerChunk = T::kOutElemsPerChunk;  // 32 (fp32) or 64 (bf16)
+    if (stores) {
 #pragma unroll
     for (int round = 0; round < kRounds; ++round) {
 #pragma unroll
@@ -651,7 +652,13 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             for (int i = 0; i < 32; ++i) o[i] = 0u;
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * inv_l);
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f_self);
+          if (split && n_tile[1] > 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              o[i] = __float_as_uint(fmaf(__uint_as_float(ld_shared_b32(xO + ((col0 + half * 32 + i) * kBlockM + r) * 4)), f_other,
+                                          __uint_as_float(o[i])));
+          }
           const uint32_t base = stage + ch * kChunkBytes + row_off;
           if constexpr (T::kOutSize == 4) {
 #pragma unroll
@@ -683,6 +690,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (round + 1 < kRounds) named_bar_sync(1 + t, 128);
     }
     if ((warp & 3) == 0 && lane == 0) tma_store_wait_all();
+    }
   }
 
   // ---- teardown ----

@@ -132,6 +132,33 @@ def test_ragged_sequence_lengths(fab, oracle, cuda_device, n, causal):
     assert np.abs(lse - lse_ref).max() < 5e-3
 
 
+@pytest.mark.parametrize("d,dtype,n,causal", [(64, torch.float32, 384, False), (64, torch.float32, 640, True), (32, torch.float32, 1024, False),
+                                              (32, torch.float32, 200, True), (128, torch.bfloat16, 896, True), (128, torch.bfloat16, 1024, False),
+                                              (64, torch.bfloat16, 128, False), (64, torch.bfloat16, 300, True)])
+def test_tail_cta_split_kv_merge(fab, oracle, cuda_device, monkeypatch, d, dtype, n, causal):
+    """A 128-row tail CTA attends the two halves of its K/V range in tile slots A and B and merges the partial
+    (O, m, l) pairs in its epilogue; with FA_B200_TAIL_SPLIT=0 it runs one slot over the whole range.  Both must match
+    the oracle, and each other to within the path's tolerance (odd tile counts, a single tile, ragged and causal tails)."""
+    q, k, v = seeded((1, 3, n, d), 70), seeded((1, 3, n, d), 71), seeded((1, 3, n, d), 72)
+    if dtype == torch.bfloat16:
+        q, k, v = _bf16_round(q), _bf16_round(k), _bf16_round(v)
+    scale = 1 / math.sqrt(d)
+    o_ref, lse_ref = oracle.f64(q, k, v, scale, causal)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("FA_B200_TAIL_SPLIT", mode)
+        outs[mode] = _run(fab, q, k, v, causal, scale, dtype=dtype)
+        assert fab.last_impl() == fab.FA_IMPL_TCGEN05
+        o, lse = outs[mode]
+        if dtype == torch.bfloat16:
+            assert np.abs(o - o_ref).max() < TOL_BF16
+        else:
+            assert tf32_err(o, o_ref) < TOL_TF32_FEWKEYS
+        assert np.abs(lse - lse_ref).max() < 5e-3
+    tol = TOL_BF16 if dtype == torch.bfloat16 else TOL_TF32_FEWKEYS
+    assert np.abs(outs["1"][0] - outs["0"][0]).max() < tol
+
+
 @pytest.mark.parametrize("nq,nk,causal", [(128, 384, False), (100, 300, True), (300, 100, False), (64, 1024, True)])
 def test_cross_lengths(fab, oracle, cuda_device, nq, nk, causal):
     q, k, v = seeded((2, nq, 64), 61), seeded((2, nk, 64), 62), seeded((2, nk, 64), 63)
