@@ -62,6 +62,10 @@
 #else
 #define FA_TRACE_AT(role, step, slot) do { } while (0)
 #endif
+// one-off CTA milestones go into the last step row of a role: (role 0/1 = softmax A/B: 0 entry, 1 setup done, 2 K/V loop
+// done, 3 O final, 4 O staged in SMEM, 5 TMA store issued+read, 6 store complete; role 2 = MMA warp: 0 entry, 1 Q full,
+// 2 K_0 full, 3 S_0 issued)
+#define FA_TRACE_MISC(role, slot) FA_TRACE_AT(role, fa::kTraceSteps - 1, slot)
 
 namespace fa {
 
@@ -133,6 +137,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) FA_TRACE_MISC(0, 0);
+  if (threadIdx.x == 128) FA_TRACE_MISC(1, 0);
+  if (warp == 9) FA_TRACE_MISC(2, 0);
 
   // ---- work assignment: blockIdx.x -> (m block, head, batch); m fastest so neighbours share K/V in L2 ----
   // Wave quantisation: the host sizes n_big to whole waves of 256-row blocks; the remainder blocks (if they are few
@@ -208,6 +215,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem_ptr));
+  if (threadIdx.x == 0) FA_TRACE_MISC(0, 1);
+  if (threadIdx.x == 128) FA_TRACE_MISC(1, 1);
 
   if (warp == 8) {
     // =========================== TMA producer ===========================
@@ -329,8 +338,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         // ---- two Q tiles share every K/V tile: ring index of K_j is 2j, of V_j is 2j+1 ----
         if (n_tile[0] > 0) mbar_wait(bar_q, 0, TAG_Q_FULL);
         if (n_tile[1] > 0) mbar_wait(bar_q + 8, 0, TAG_Q_FULL);
+        FA_TRACE_MISC(2, 1);
         wait_full(0);
         tc_fence_after();
+        FA_TRACE_MISC(2, 2);
         if (elect_one_sync()) {
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
@@ -342,6 +353,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           tc_commit(bar_empty + 0);
         }
         __syncwarp();
+        FA_TRACE_MISC(2, 3);
         for (int j = 0; j < n_max; ++j) {
           const int iv = 2 * j + 1, ik = 2 * j + 2;
           const int vbuf = iv % T::kNBuf, kbuf = ik % T::kNBuf;
@@ -580,10 +592,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     }
 
     // ---- epilogue: O/l -> swizzled SMEM (reusing this tile's Q buffer) -> TMA store; LSE -> global ----
+    if (tracer) FA_TRACE_MISC(t, 2);
     if (n_mine > 0) {
       mbar_wait(bar_o + 8 * t, 0, TAG_O_FINAL);
       tc_fence_after();
     }
+    if (tracer) FA_TRACE_MISC(t, 3);
     // scale of this slot's accumulator and of the partner's partial (split-KV tail CTAs only) in the final O
     float f_self = (n_mine > 0 && l > 0.f) ? 1.0f / l : 0.f;
     float f_other = 0.f;
@@ -679,6 +693,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
       fence_proxy_async_smem();
       named_bar_sync(1 + t, 128);
+      if (tracer) FA_TRACE_MISC(t, 4);
       if ((warp & 3) == 0 && lane == 0) {
 #pragma unroll
         for (int ch = 0; ch < T::kDChunks; ++ch)
@@ -686,10 +701,14 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                        batch);
         tma_store_commit();
         tma_store_wait_read();
+        FA_TRACE_MISC(t, 5);
       }
       if (round + 1 < kRounds) named_bar_sync(1 + t, 128);
     }
-    if ((warp & 3) == 0 && lane == 0) tma_store_wait_all();
+    if ((warp & 3) == 0 && lane == 0) {
+      tma_store_wait_all();
+      FA_TRACE_MISC(t, 6);
+    }
     }
   }
 

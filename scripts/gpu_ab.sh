@@ -7,9 +7,9 @@ L=gpurun_out/ab.log
 : > $L
 for v in $(ls flashattention.c_b200/variants); do
   export LD_LIBRARY_PATH=$PWD/flashattention.c_b200/variants/$v
-  if [ "$v" = "T" ]; then
-    FA_B200_TRACE=gpurun_out/trace_v7_c4.txt timeout 120 $H/fa_check bf16 128 128 8192 0 0 2 0 > /dev/null
-    FA_B200_TRACE=gpurun_out/trace_v7_c2.txt timeout 120 $H/fa_check f32 64 16 8192 0 0 2 0 > /dev/null
+  if [[ "$v" == T* ]]; then
+    FA_B200_TRACE=gpurun_out/trace_c4.txt timeout 120 $H/fa_check bf16 128 128 8192 0 0 2 0 > /dev/null
+    FA_B200_TRACE=gpurun_out/trace_c2.txt timeout 120 $H/fa_check f32 64 16 8192 0 0 2 0 > /dev/null
     continue
   fi
   echo "#### variant $v" >> $L
