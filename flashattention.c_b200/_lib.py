@@ -16,6 +16,7 @@ EXPORTED_SYMBOLS = [
     "fa_forward", "fa_forward_ex", "fa_forward_packed_qkv", "fa_forward_host", "fa_merge_partials", "fa_cast_f32_to_bf16",
     "run_flash_tiled_coarse", "run_flash_tiled_coarse_causal", "attention_forward6", "attention_forward",
     "fa_strerror", "fa_last_cuda_error", "fa_last_impl", "fa_version", "fa_launch_count",
+    "fa_watchdog_info",
 ]
 
 
@@ -69,6 +70,8 @@ def lib() -> ctypes.CDLL:
         L.fa_last_impl.restype = ctypes.c_int
         L.fa_version.restype = ctypes.c_int
         L.fa_launch_count.restype = ctypes.c_int64
+        L.fa_watchdog_info.argtypes = [ctypes.POINTER(ctypes.c_uint32)]
+        L.fa_watchdog_info.restype = ctypes.c_int
         _lib = L
     return _lib
 

@@ -65,6 +65,58 @@ int current_sm_count() {
   return g_dev[dev].checked ? g_dev[dev].sms : 148;
 }
 
+// ---- work counters of the persistent kernel: {next item, CTAs finished}; the last CTA of a launch zeroes its pair, so a
+// pair is reusable as soon as the launch that used it has finished.  Launches rotate through a per-device pool so that
+// kernels running concurrently on different streams never share a pair (up to kCounterPool launches in flight).
+constexpr int kCounterPool = 256;
+struct CounterPool { unsigned int* base = nullptr; std::atomic<unsigned int> next{0}; };
+CounterPool g_counters[64];
+std::mutex g_counters_mu;
+
+// host-mapped record of the first mbarrier watchdog expiry (see ptx.cuh); one per process, shared by all devices
+unsigned int* g_wd_host = nullptr;
+bool g_wd_installed[64] = {};
+std::mutex g_wd_mu;
+void install_watchdog_record(int dev) {
+  if (dev < 0 || dev >= 64 || g_wd_installed[dev]) return;
+  std::lock_guard<std::mutex> lk(g_wd_mu);
+  if (g_wd_installed[dev]) return;
+  if (!g_wd_host) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&g_wd_host), 4 * sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      g_wd_host = nullptr;
+    } else {
+      memset(g_wd_host, 0, 4 * sizeof(unsigned int));
+    }
+  }
+  if (g_wd_host) {
+    unsigned int* dptr = nullptr;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), g_wd_host, 0) == cudaSuccess)
+      cudaMemcpyToSymbol(fa::g_fa_watchdog_host, &dptr, sizeof(dptr));
+    cudaGetLastError();
+  }
+  g_wd_installed[dev] = true;
+}
+
+int next_work_counter(unsigned int** out) {
+  int dev = 0;
+  FA_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return FA_ERR_NO_DEVICE;
+  install_watchdog_record(dev);
+  CounterPool& cp = g_counters[dev];
+  if (!cp.base) {
+    std::lock_guard<std::mutex> lk(g_counters_mu);
+    if (!cp.base) {
+      unsigned int* b = nullptr;
+      FA_CUDA(cudaMalloc(&b, kCounterPool * 2 * sizeof(unsigned int)));
+      FA_CUDA(cudaMemset(b, 0, kCounterPool * 2 * sizeof(unsigned int)));   // synchronous w.r.t. the host: done before any launch
+      cp.base = b;
+    }
+  }
+  *out = cp.base + 2 * (cp.next.fetch_add(1, std::memory_order_relaxed) % kCounterPool);
+  return FA_OK;
+}
+
 // ---- cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -148,7 +200,8 @@ int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& m
     FA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kSmemBytes));
     attr_set[dev] = true;
   }
-  const int64_t grid = (int64_t)fp.n_big + 2 * ((int64_t)fp.num_m_blocks * fp.heads * fp.batch - fp.n_big);
+  // one persistent CTA per SM pulling items from the work counter (fp.work_counter != nullptr), or one CTA per item
+  const int64_t grid = fp.work_counter ? std::min<int64_t>(fp.n_items, std::max(1, current_sm_count())) : (int64_t)fp.n_items;
   if (grid <= 0 || grid > 0x7fffffff) return FA_ERR_INVALID_ARG;
   kern<<<(unsigned)grid, fa::kNumThreads, T::kSmemBytes, st>>>(mq, mk, mv, mo, fp);
   FA_CUDA(cudaGetLastError());
@@ -210,6 +263,15 @@ int run_tc(const fa_params* p, cudaStream_t st) {
     // the remainder CTAs split their K/V range over the two tile slots (FA_B200_TAIL_SPLIT=0: one slot, A/B aid)
     const char* ts = getenv("FA_B200_TAIL_SPLIT");   // read per call so a test can compare both modes in one process
     fp.tail_split = (ts && atoi(ts) == 0) ? 0 : 1;
+    const int64_t n_items = n_big + 2 * (nb - n_big);
+    if (n_items > 0x7fffffff) return FA_ERR_INVALID_ARG;
+    fp.n_items = (int)n_items;
+    // persistent CTAs take items from a device counter (FA_B200_PERSISTENT=0: one CTA per item, hardware-scheduled)
+    const char* ps = getenv("FA_B200_PERSISTENT");
+    fp.work_counter = nullptr;
+    if (!(ps && atoi(ps) == 0)) {
+      if ((rc = next_work_counter(&fp.work_counter))) return rc;
+    }
   }
   fp.v_desc_hi = fa::make_sdesc_hi(v_lbo, v_sbo, v_layout);
   fp.trace = nullptr;
@@ -312,6 +374,11 @@ int fa_version(void) { return FA_B200_VERSION; }
 const char* fa_last_cuda_error(void) { return t_cuda_err; }
 int fa_last_impl(void) { return t_last_impl; }
 int64_t fa_launch_count(void) { return g_launches.load(); }
+int fa_watchdog_info(uint32_t out[4]) {
+  if (!out) return FA_ERR_INVALID_ARG;
+  for (int i = 0; i < 4; ++i) out[i] = g_wd_host ? g_wd_host[i] : 0u;
+  return FA_OK;
+}
 
 const char* fa_strerror(int status) {
   switch (status) {

@@ -8,29 +8,35 @@
 //   O += P V      (FA:326-340)           -> tcgen05.mma, A = P read straight from TMEM, B = V (MN-major) from SMEM
 //   epilogue      (FA:346-354)           -> O/l -> swizzled SMEM -> TMA store (128-byte coalesced)
 //
-// One CTA owns 256 query rows of one (batch, head) as two 128-row tiles A and B that ping-pong on the
-// tensor pipe: while the softmax warps of one tile work on S_j, the MMA thread runs P*V and the next
-// Q*K^T of the other tile.
+// Work items.  An item is 256 query rows of one (batch, head): two 128-row tiles in tile slots A and B that
+// ping-pong on the tensor pipe — while the softmax warps of one slot work on S_j, the tensor pipe runs P*V and the
+// next Q*K^T of the other.  The host sizes the item list as whole waves of 256-row items plus a remainder wave of
+// 128-row items.  A 128-row item runs in "split-KV" mode: slot A attends the first half of the K/V tiles and slot B
+// the second half (same Q rows), so the two halves ping-pong exactly like two Q tiles do, and the partial (O, m, l)
+// pairs are merged by the log-sum-exp rule in the epilogue (slot A reads O_B straight from TMEM: both slots use the
+// same TMEM lanes, different columns).  The serial chain of a tail item is therefore half as long.
 //
-// Warp roles (320 threads): warps 0-3 softmax/epilogue of tile A, 4-7 of tile B (warp w reads TMEM lanes
-// 32*(w%4)..+31), warp 8 lane 0 = TMA producer (+ TMEM alloc/dealloc by the whole warp), warp 9 = MMA issuer
-// (converged warp, one elected lane issues A then B in order).  `tcgen05.mma` issue back-pressures at the rate the
-// tensor pipe retires (~64 cycles per 128x128x16 MMA) and every mbarrier wait + tcgen05 fence costs ~200 cycles
+// Persistent CTAs.  The grid is one CTA per SM; every CTA loops over items it takes from a global atomic counter
+// (heaviest causal blocks first), so TMEM, barriers and tensor maps are set up once per SM, the TMA producer runs ahead
+// into the next item's K/V (and Q, where SMEM has room for a second Q set) while the current item is still in its
+// K/V loop or epilogue, and causal work stays balanced.  The item index travels from the producer to the other warps
+// through a small SMEM queue (bar_wfull / bar_wempty).  With FwdParams::work_counter == nullptr items are taken with
+// a static stride instead (one item per CTA when the grid is as large as the item list).
+//
+// Warp roles (320 threads): warps 0-3 softmax/epilogue of slot A, 4-7 of slot B (warp w reads TMEM lanes
+// 32*(w%4)..+31), warp 8 lane 0 = TMA producer + item fetch (+ TMEM alloc/dealloc by the whole warp), warp 9 = MMA
+// issuer (converged warp, one elected lane issues A then B in order).  `tcgen05.mma` issue back-pressures at the rate
+// the tensor pipe retires (~64 cycles per 128x128x16 MMA) and every mbarrier wait + tcgen05 fence costs ~200 cycles
 // even when already complete (measured: profiles/r01_trace_v1_c4_report.txt), so waits are batched.  Two
-// independent issuer warps (one per tile) were measured and rejected: the tiles fall into lock-step
+// independent issuer warps (one per slot) were measured and rejected: the slots fall into lock-step
 // (profiles/r01_ab_issuer_modes_session9.log).
-//
-// Tail CTAs.  The host sizes the grid as whole waves of 256-row CTAs plus a remainder wave of 128-row CTAs.  A
-// remainder CTA runs its one Q tile in "split-KV" mode: tile slot A attends the first half of the K/V tiles and
-// slot B the second half (same Q rows), so the two halves ping-pong on the tensor pipe exactly like two Q tiles
-// do, and the partial (O, m, l) pairs are merged by the log-sum-exp rule through SMEM in the epilogue.  The serial
-// chain of a tail CTA is therefore half as long (C1 is nothing but tail CTAs).
 //
 // TMEM columns (512 allocated): S_A [0,128)  S_B [128,256)  O_A [256,256+d)  O_B [256+d, 256+2d).
 // P aliases S: bf16 path packs two bf16 per column into S cols [0,64); tf32 path overwrites S in place.
 //
-// SMEM (dynamic, 1024-B aligned): Q_A | Q_B | ring of NBUF K/V tiles | barriers.  Every tile is DCHUNKS
-// boxes of [128 rows x 128 bytes] in the SWIZZLE_128B layout that TMA writes and the UMMA descriptors read.
+// SMEM (dynamic, 1024-B aligned): kQSets x (Q_A | Q_B) | ring of NBUF K/V tiles | barriers | work queue | (m, l)
+// exchange.  Every tile is DCHUNKS boxes of [128 rows x 128 bytes] in the SWIZZLE_128B layout that TMA writes and
+// the UMMA descriptors read.  A slot's Q buffer doubles as the staging buffer of its O tile for the TMA store.
 #pragma once
 #include "ptx.cuh"
 
@@ -79,8 +85,10 @@ struct FwdParams {
   uint64_t v_desc_hi; // upper descriptor bits (LBO/SBO/layout) of V as the MN-major B operand of P*V
   unsigned long long* trace;  // FA_TRACE builds only; nullptr otherwise
   int n_big;          // CTAs [0, n_big) own a 256-row block (tiles A+B); CTAs beyond own a 128-row half block
-  int tail_split;     // != 0: a 128-row CTA splits its K/V range over tile slots A and B (merged in the epilogue);
+  int tail_split;     // != 0: a 128-row item splits its K/V range over tile slots A and B (merged in the epilogue);
                       // 0: it runs slot A only
+  int n_items;        // n_big + 2 * (number of 256-row blocks run as pairs of 128-row items)
+  unsigned int* work_counter;   // [0] next item, [1] CTAs finished (the last one resets both); nullptr: static stride
 };
 constexpr int kTraceSteps = 48;
 
@@ -88,7 +96,8 @@ constexpr int kBlockM = 128;          // rows per Q tile
 constexpr int kBlockN = 128;          // keys per K/V tile
 constexpr int kChunkBytes = 128 * 128;  // one TMA box: 128 rows x 128 bytes
 constexpr int kNumThreads = 320;      // 8 softmax warps + TMA producer warp + MMA-issuer warp
-constexpr int kBarMerge = 3;          // named barrier: slot B hands its partial (O, m, l) to slot A (split-KV tail CTAs)
+constexpr int kBarMerge = 3;          // named barrier: slot B hands its partial (m, l) to slot A (split-KV tail items)
+constexpr int kWorkQueue = 4;         // depth of the SMEM item queue (the producer is at most two items ahead)
 constexpr float kRescaleThreshold = 8.0f;  // lazy rescale: keep a stale max while it is within 2^8
 
 template <bool kTF32, int kHeadDim, bool kOutF32>
@@ -102,9 +111,12 @@ struct FwdTraits {
   static constexpr int kTileBytes = kDChunks * kChunkBytes;
   static constexpr int kNBuf = kDChunks == 1 ? 8 : 5;          // K/V ring depth (tiles)
   static constexpr int kUmmaK = 32 / kInSize;                  // K per tcgen05.mma: 8 (tf32) / 16 (bf16)
-  static constexpr int kSmemData = (2 + kNBuf) * kTileBytes;
-  static constexpr int kNumBarriers = 2 /*q*/ + 2 * kNBuf + 2 /*s_full*/ + 4 /*p_full halves*/ + 2 /*o_final*/;
-  static constexpr int kSmemBytes = kSmemData + kNumBarriers * 8 + 16 /*tmem ptr*/ + 1024 /*alignment slack*/;
+  static constexpr int kQSets = kDChunks == 1 ? 2 : 1;         // Q double-buffered across items where SMEM allows
+  static constexpr int kSmemData = (2 * kQSets + kNBuf) * kTileBytes;
+  static constexpr int kNumBarriers = 4 * kQSets /*q full, q free*/ + 2 * kNBuf + 2 /*s_full*/ + 4 /*p_full halves*/ +
+                                      2 /*o_final*/ + 2 /*o_free*/ + 2 * kWorkQueue;
+  static constexpr int kSmemBytes = kSmemData + kNumBarriers * 8 + 16 /*tmem ptr*/ + kWorkQueue * 4 + 2 * kBlockM * 4 /*m, l*/ +
+                                    1024 /*alignment slack*/;
   static constexpr int kTmemS = 0;        // + 128*t
   static constexpr int kTmemO = 256;      // + kHeadDim*t
   static_assert(kDChunks == 1 || kDChunks == 2, "tile row must be 128 or 256 bytes");
@@ -113,8 +125,60 @@ struct FwdTraits {
 
 // watchdog tags
 enum : uint32_t {
-  TAG_Q_FULL = 1, TAG_KV_FULL = 2, TAG_KV_EMPTY = 3, TAG_S_FULL = 4, TAG_P_FULL = 5, TAG_O_FINAL = 6
+  TAG_Q_FULL = 1, TAG_KV_FULL = 2, TAG_KV_EMPTY = 3, TAG_S_FULL = 4, TAG_P_FULL = 5, TAG_O_FINAL = 6, TAG_Q_FREE = 7,
+  TAG_O_FREE = 8, TAG_W_FULL = 9, TAG_W_EMPTY = 10
 };
+
+// What one work item is, derived from its index by every warp role on its own.
+struct Item {
+  int head, batch, row0;   // first query row of slot A
+  int row1;                // first query row of slot B (== row0 in split mode)
+  bool single, split;
+  int n0, n1;              // K/V tiles of slot A / slot B (scalars: a runtime-indexed array would live in local memory)
+  int kv_first1;           // first K/V tile of slot B (split mode), else 0
+  int n_max;
+  FA_DEVINL int n(int t) const { return t == 0 ? n0 : n1; }
+};
+template <bool kCausal>
+FA_DEVINL Item decode_item(const FwdParams& p, int bid) {
+  Item it;
+  it.single = bid >= p.n_big;
+  int half = 0;
+  if (it.single) {
+    const int k = bid - p.n_big;
+    half = k & 1;
+    bid = p.n_big + (k >> 1);
+  }
+  int m_blk = bid % p.num_m_blocks;   // m fastest so neighbours share K/V in L2
+  bid /= p.num_m_blocks;
+  it.head = bid % p.heads;
+  it.batch = bid / p.heads;
+  if (kCausal) m_blk = p.num_m_blocks - 1 - m_blk;  // heaviest blocks first
+  it.row0 = m_blk * (2 * kBlockM) + half * kBlockM;
+  it.split = it.single && p.tail_split != 0;   // slots A and B = two halves of the K/V range of ONE Q tile
+  const int n_kv_total = (p.n_k + kBlockN - 1) / kBlockN;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int r0 = it.row0 + t * kBlockM;
+    int n = n_kv_total;
+    if (kCausal) {
+      const int last_key = r0 + kBlockM - 1 + p.causal_offset;
+      n = last_key < 0 ? 0 : min(n_kv_total, last_key / kBlockN + 1);
+    }
+    if (r0 >= p.n_q || (it.single && t == 1)) n = 0;
+    if (t == 0) it.n0 = n; else it.n1 = n;
+  }
+  it.kv_first1 = 0;
+  if (it.split) {
+    const int n = it.n0;
+    it.n0 = (n + 1) >> 1;
+    it.n1 = n - it.n0;
+    it.kv_first1 = it.n0;
+  }
+  it.n_max = max(it.n0, it.n1);
+  it.row1 = it.split ? it.row0 : it.row0 + kBlockM;
+  return it;
+}
 
 template <bool kTF32, int kHeadDim, bool kCausal, bool kOutF32>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -122,18 +186,25 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                     const FwdParams p) {
   using T = FwdTraits<kTF32, kHeadDim, kOutF32>;
+  constexpr int kQS = T::kQSets;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base;                        // 2 tiles
-  const uint32_t sKV = smem_base + 2 * T::kTileBytes;   // kNBuf tiles
+  const uint32_t sQ = smem_base;                              // [kQS][2] tiles
+  const uint32_t sKV = smem_base + 2 * kQS * T::kTileBytes;   // kNBuf tiles
   const uint32_t sBar = smem_base + T::kSmemData;
-  const uint32_t bar_q = sBar;                          // [2]
-  const uint32_t bar_full = sBar + 16;                  // [kNBuf]
-  const uint32_t bar_empty = bar_full + 8 * T::kNBuf;   // [kNBuf]
-  const uint32_t bar_s = bar_empty + 8 * T::kNBuf;      // [2]
-  const uint32_t bar_p = bar_s + 16;                    // [tile][half] = [4]
-  const uint32_t bar_o = bar_p + 32;                    // [2]
-  const uint32_t s_tmem_ptr = bar_o + 16;
+  const uint32_t bar_q = sBar;                                // [kQS][2]  Q tile landed
+  const uint32_t bar_qfree = bar_q + 16 * kQS;                // [kQS][2]  Q buffer (= O staging) reusable
+  const uint32_t bar_full = bar_qfree + 16 * kQS;             // [kNBuf]
+  const uint32_t bar_empty = bar_full + 8 * T::kNBuf;         // [kNBuf]
+  const uint32_t bar_s = bar_empty + 8 * T::kNBuf;            // [2]
+  const uint32_t bar_p = bar_s + 16;                          // [slot][half] = [4]
+  const uint32_t bar_o = bar_p + 32;                          // [2]  O_t final
+  const uint32_t bar_ofree = bar_o + 16;                      // [2]  slot t's epilogue has read its accumulator(s) out of TMEM
+  const uint32_t bar_wfull = bar_ofree + 16;                  // [kWorkQueue]
+  const uint32_t bar_wempty = bar_wfull + 8 * kWorkQueue;     // [kWorkQueue]
+  const uint32_t s_tmem_ptr = bar_wempty + 8 * kWorkQueue;    // 16 bytes
+  const uint32_t s_work = s_tmem_ptr + 16;                    // [kWorkQueue] item indices (-1 = no more work)
+  const uint32_t s_ml = s_work + 4 * kWorkQueue;              // m[128], l[128] of slot B (split-KV merge)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -141,53 +212,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (threadIdx.x == 128) FA_TRACE_MISC(1, 0);
   if (warp == 9) FA_TRACE_MISC(2, 0);
 
-  // ---- work assignment: blockIdx.x -> (m block, head, batch); m fastest so neighbours share K/V in L2 ----
-  // Wave quantisation: the host sizes n_big to whole waves of 256-row blocks; the remainder blocks (if they are few
-  // enough) are issued as pairs of 128-row CTAs so the last, partial wave is short.
-  int bid = blockIdx.x;
-  const bool single_tile = bid >= p.n_big;
-  int half = 0;
-  if (single_tile) {
-    const int k = bid - p.n_big;
-    half = k & 1;
-    bid = p.n_big + (k >> 1);
-  }
-  int m_blk = bid % p.num_m_blocks;
-  bid /= p.num_m_blocks;
-  const int head = bid % p.heads;
-  const int batch = bid / p.heads;
-  if (kCausal) m_blk = p.num_m_blocks - 1 - m_blk;  // heaviest blocks first
-  const int row0 = m_blk * (2 * kBlockM) + half * kBlockM;
-  const bool split = single_tile && p.tail_split != 0;   // slots A and B = two halves of the K/V range of ONE Q tile
-
-  // KV trip count and first K/V tile of each tile slot
-  const int n_kv_total = (p.n_k + kBlockN - 1) / kBlockN;
-  int n_tile[2];
-  int kv_first[2] = {0, 0};
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int r0 = row0 + t * kBlockM;
-    int n = n_kv_total;
-    if (kCausal) {
-      const int last_key = r0 + kBlockM - 1 + p.causal_offset;
-      n = last_key < 0 ? 0 : min(n_kv_total, last_key / kBlockN + 1);
-    }
-    if (r0 >= p.n_q || (single_tile && t == 1)) n = 0;
-    n_tile[t] = n;
-  }
-  if (split) {
-    const int n = n_tile[0];
-    n_tile[0] = (n + 1) >> 1;
-    n_tile[1] = n - n_tile[0];
-    kv_first[1] = n_tile[0];
-  }
-  const int n_max = max(n_tile[0], n_tile[1]);
-  const int row_of_tile1 = split ? row0 : row0 + kBlockM;   // first Q row of slot B
-
   // ---- one-time setup ----
   if (warp == 9 && lane == 0) {
-    mbar_init(bar_q, 1);
-    mbar_init(bar_q + 8, 1);
+    for (int i = 0; i < 2 * kQS; ++i) {
+      mbar_init(bar_q + 8 * i, 1);
+      mbar_init(bar_qfree + 8 * i, 1);
+    }
     for (int i = 0; i < T::kNBuf; ++i) {
       mbar_init(bar_full + 8 * i, 1);
       mbar_init(bar_empty + 8 * i, 1);
@@ -197,6 +227,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_init(bar_p + 16 * t, 128);
       mbar_init(bar_p + 16 * t + 8, 128);
       mbar_init(bar_o + 8 * t, 1);
+    }
+    mbar_init(bar_ofree, 4);              // one arrival per softmax warp of the slot, only in items where it read TMEM
+    mbar_init(bar_ofree + 8, 4);
+    for (int i = 0; i < kWorkQueue; ++i) {
+      mbar_init(bar_wfull + 8 * i, 1);
+      mbar_init(bar_wempty + 8 * i, 9);   // MMA warp + 8 softmax warps
     }
     fence_mbar_init();
   }
@@ -218,293 +254,318 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (threadIdx.x == 0) FA_TRACE_MISC(0, 1);
   if (threadIdx.x == 128) FA_TRACE_MISC(1, 1);
 
+  // consumer side of the item queue: every lane of the warp reads the item, one lane releases the queue slot
+  auto next_item = [&](int seq) -> int {
+    if (seq == 0) return static_cast<int>(blockIdx.x);
+    const int ws = seq % kWorkQueue;
+    // queue slot 0 is first used by seq = kWorkQueue (seq 0 bypasses the queue), the others by seq = ws
+    mbar_wait(bar_wfull + 8 * ws, (seq / kWorkQueue - (ws == 0 ? 1 : 0)) & 1, TAG_W_FULL);
+    const int item = static_cast<int>(ld_shared_b32(s_work + 4 * ws));
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_wempty + 8 * ws);
+    return item;
+  };
+
   if (warp == 8) {
-    // =========================== TMA producer ===========================
-    if (lane == 0 && n_max > 0) {
-      // Q: one tile per slot; in split mode both slots read the same Q tile from buffer 0
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (n_tile[t] > 0 && !(split && t == 1)) {
-          mbar_arrive_expect_tx(bar_q + 8 * t, T::kTileBytes);
+    // =========================== item fetch + TMA producer ===========================
+    if (lane == 0) {
+      int ring = 0;   // running index into the K/V ring; the MMA issuer consumes tiles in exactly this order
+      for (int seq = 0;; ++seq) {
+        // the first item of a CTA is its block index (no round trip to the counter on the critical start-up path, and
+        // no queue: every role knows it); later items come from the counter, or from a static stride without one
+        int item = static_cast<int>(blockIdx.x);
+        if (seq > 0) {
+          if (p.work_counter != nullptr) item = static_cast<int>(gridDim.x + atomicAdd(p.work_counter, 1u));
+          else item = static_cast<int>(blockIdx.x) + seq * static_cast<int>(gridDim.x);
+          if (item >= p.n_items) item = -1;
+          const int ws = seq % kWorkQueue;
+          const int use = seq / kWorkQueue - (ws == 0 ? 1 : 0);   // how often this queue slot has been used before
+          if (use > 0) mbar_wait(bar_wempty + 8 * ws, (use - 1) & 1, TAG_W_EMPTY);
+          st_shared_b32(s_work + 4 * ws, static_cast<uint32_t>(item));
+          mbar_arrive(bar_wfull + 8 * ws);
+        }
+        if (item < 0) break;
+        const Item w = decode_item<kCausal>(p, item);
+        if (w.n_max == 0) continue;
+        const int set = seq % kQS;
+        auto load_kv = [&](const CUtensorMap* tm, int kv_tile) {
+          const int buf = ring % T::kNBuf;
+          const int round = ring / T::kNBuf;
+          ++ring;
+          if (round > 0) mbar_wait(bar_empty + 8 * buf, (round - 1) & 1, TAG_KV_EMPTY);
+          mbar_arrive_expect_tx(bar_full + 8 * buf, T::kTileBytes);
 #pragma unroll
           for (int c = 0; c < T::kDChunks; ++c)
-            tma_load_4d(sQ + t * T::kTileBytes + c * kChunkBytes, &tm_q, bar_q + 8 * t, c * T::kElemsPerChunk,
-                        row0 + t * kBlockM, head, batch);
-        }
-      }
-      int ring = 0;   // running index into the K/V ring; the MMA issuer consumes tiles in exactly this order
-      auto load = [&](const CUtensorMap* tm, int kv_tile) {
-        const int buf = ring % T::kNBuf;
-        const int round = ring / T::kNBuf;
-        ++ring;
-        if (round > 0) mbar_wait(bar_empty + 8 * buf, (round - 1) & 1, TAG_KV_EMPTY);
-        mbar_arrive_expect_tx(bar_full + 8 * buf, T::kTileBytes);
+            tma_load_4d(sKV + buf * T::kTileBytes + c * kChunkBytes, tm, bar_full + 8 * buf, c * T::kElemsPerChunk,
+                        kv_tile * kBlockN, w.head, w.batch);
+        };
+        // Q: one tile per slot; in split mode both slots read the same Q tile from slot A's buffer.  The buffer is
+        // free once the epilogue that staged its O tile there (kQS items ago) has been read out by the TMA store.
+        auto load_q = [&]() {
 #pragma unroll
-        for (int c = 0; c < T::kDChunks; ++c)
-          tma_load_4d(sKV + buf * T::kTileBytes + c * kChunkBytes, tm, bar_full + 8 * buf, c * T::kElemsPerChunk,
-                      kv_tile * kBlockN, head, batch);
-      };
-      if (!split) {
-        for (int j = 0; j < n_max; ++j) {   // K_0, V_0, K_1, V_1, ... shared by both Q tiles
-          load(&tm_k, j);
-          load(&tm_v, j);
+          for (int t = 0; t < 2; ++t) {
+            if (w.n(t) > 0 && !(w.split && t == 1)) {
+              const int qb = set * 2 + t;
+              if (seq >= kQS) mbar_wait(bar_qfree + 8 * qb, (seq / kQS - 1) & 1, TAG_Q_FREE);
+              mbar_arrive_expect_tx(bar_q + 8 * qb, T::kTileBytes);
+#pragma unroll
+              for (int c = 0; c < T::kDChunks; ++c)
+                tma_load_4d(sQ + qb * T::kTileBytes + c * kChunkBytes, &tm_q, bar_q + 8 * qb, c * T::kElemsPerChunk,
+                            w.row0 + t * kBlockM, w.head, w.batch);
+            }
+          }
+        };
+        // The first kNBuf K/V tiles only need ring slots that the previous item releases on its own, so they are
+        // issued before the Q tiles (whose buffer may still hold the previous item's O on its way out).
+        int issued = 0;
+        bool q_done = false;
+        auto kv = [&](const CUtensorMap* tm, int kv_tile) {
+          if (!q_done && issued == T::kNBuf) {
+            load_q();
+            q_done = true;
+          }
+          load_kv(tm, kv_tile);
+          ++issued;
+        };
+        // With two Q sets the buffer is free long before (its O left two items ago) and on the very first item there is
+        // nothing to wait for: Q first, it is needed first.  With one set the previous item's O is still on its way out.
+        if (seq == 0 || kQS > 1) {
+          load_q();
+          q_done = true;
         }
-      } else {
-        // K_A0, K_B0, then per step: V_A(j), K_A(j+1), V_B(j), K_B(j+1)
-        const int nA = n_tile[0], nB = n_tile[1];
-        load(&tm_k, 0);
-        if (nB > 0) load(&tm_k, nA);
-        for (int j = 0; j < nA; ++j) {
-          load(&tm_v, j);
-          if (j + 1 < nA) load(&tm_k, j + 1);
-          if (j < nB) {
-            load(&tm_v, nA + j);
-            if (j + 1 < nB) load(&tm_k, nA + j + 1);
+        if (!w.split) {
+          for (int j = 0; j < w.n_max; ++j) {   // K_0, V_0, K_1, V_1, ... shared by both Q tiles
+            kv(&tm_k, j);
+            kv(&tm_v, j);
+          }
+        } else {
+          // K_A0, K_B0, then per step: V_A(j), K_A(j+1), V_B(j), K_B(j+1)
+          const int nA = w.n0, nB = w.n1;
+          kv(&tm_k, 0);
+          if (nB > 0) kv(&tm_k, nA);
+          for (int j = 0; j < nA; ++j) {
+            kv(&tm_v, j);
+            if (j + 1 < nA) kv(&tm_k, j + 1);
+            if (j < nB) {
+              kv(&tm_v, nA + j);
+              if (j + 1 < nB) kv(&tm_k, nA + j + 1);
+            }
           }
         }
+        if (!q_done) load_q();
       }
     }
   } else if (warp == 9) {
     // =========================== MMA issuer ===========================
     // The whole warp follows the (warp-uniform) control flow and waits on the mbarriers; one elected lane issues.
-    if (n_max > 0) {
-      constexpr uint32_t kFmt = kTF32 ? 2u : 1u;
-      constexpr uint32_t idesc_s = make_idesc(kFmt, 0, kBlockM, kBlockN);
-      constexpr uint32_t idesc_pv = make_idesc(kFmt, 1, kBlockM, kHeadDim);
-      // K-major operands (Q, K): LBO unused for swizzled K-major (encoded 1), SBO = 1024 B between 8-row groups
-      constexpr uint64_t hi_kmajor = make_sdesc_hi_sw128(16, 1024);
-      // MN-major operand (V as B of P*V): LBO = stride between 128-byte column chunks (one TMA box), SBO = stride
-      // between key groups.  bf16: SWIZZLE_128B, 8-key groups of 1024 B.  tf32: tcgen05 only accepts the
-      // SWIZZLE_128B_BASE32B layout for MN-major 32-bit operands (4-key groups of 512 B), which TMA writes with
-      // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  Built on the host next to the matching tensor map.
-      const uint64_t hi_mnmajor = p.v_desc_hi;
-      constexpr int kKStepsS = kHeadDim / T::kUmmaK;   // k-steps of Q K^T (32 bytes each)
-      constexpr int kKStepsPV = kBlockN / T::kUmmaK;   // k-steps of P V (UmmaK keys each)
-      // Descriptors are built once per operand tile; a k-step only adds to the 14-bit start-address field
-      // ((bytes >> 4); SMEM addresses are < 2^18, so the field never carries).
-      auto issue_s = [&](int t, int qbuf, int buf) {
-        const uint64_t qd = sdesc_at(hi_kmajor, sQ + qbuf * T::kTileBytes);
-        const uint64_t kd = sdesc_at(hi_kmajor, sKV + buf * T::kTileBytes);
-        const uint32_t d = tmem_base + T::kTmemS + t * kBlockN;
+    constexpr uint32_t kFmt = kTF32 ? 2u : 1u;
+    constexpr uint32_t idesc_s = make_idesc(kFmt, 0, kBlockM, kBlockN);
+    constexpr uint32_t idesc_pv = make_idesc(kFmt, 1, kBlockM, kHeadDim);
+    // K-major operands (Q, K): LBO unused for swizzled K-major (encoded 1), SBO = 1024 B between 8-row groups
+    constexpr uint64_t hi_kmajor = make_sdesc_hi_sw128(16, 1024);
+    // MN-major operand (V as B of P*V): LBO = stride between 128-byte column chunks (one TMA box), SBO = stride
+    // between key groups.  bf16: SWIZZLE_128B, 8-key groups of 1024 B.  tf32: tcgen05 only accepts the
+    // SWIZZLE_128B_BASE32B layout for MN-major 32-bit operands (4-key groups of 512 B), which TMA writes with
+    // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  Built on the host next to the matching tensor map.
+    const uint64_t hi_mnmajor = p.v_desc_hi;
+    constexpr int kKStepsS = kHeadDim / T::kUmmaK;   // k-steps of Q K^T (32 bytes each)
+    constexpr int kKStepsPV = kBlockN / T::kUmmaK;   // k-steps of P V (UmmaK keys each)
+    // Descriptors are built once per operand tile; a k-step only adds to the 14-bit start-address field
+    // ((bytes >> 4); SMEM addresses are < 2^18, so the field never carries).
+    auto issue_s = [&](int t, int qbuf, int buf) {
+      const uint64_t qd = sdesc_at(hi_kmajor, sQ + qbuf * T::kTileBytes);
+      const uint64_t kd = sdesc_at(hi_kmajor, sKV + buf * T::kTileBytes);
+      const uint32_t d = tmem_base + T::kTmemS + t * kBlockN;
 #pragma unroll
-        for (int kk = 0; kk < kKStepsS; ++kk) {
-          const uint32_t off16 = ((kk >> 2) * kChunkBytes + (kk & 3) * 32) >> 4;
-          mma_ss<kTF32>(d, qd + off16, kd + off16, idesc_s, kk > 0 ? 1u : 0u);
-        }
-      };
-      // P*V for k-steps [ks0, ks1) of the 128-key tile; A = P_t read from TMEM (it aliases S_t)
-      auto issue_pv = [&](int t, int buf, bool accumulate, int ks0, int ks1) {
-        const uint64_t vd = sdesc_at(hi_mnmajor, sKV + buf * T::kTileBytes);
-        const uint32_t d = tmem_base + T::kTmemO + t * kHeadDim;
-        const uint32_t a = tmem_base + T::kTmemS + t * kBlockN;
+      for (int kk = 0; kk < kKStepsS; ++kk) {
+        const uint32_t off16 = ((kk >> 2) * kChunkBytes + (kk & 3) * 32) >> 4;
+        mma_ss<kTF32>(d, qd + off16, kd + off16, idesc_s, kk > 0 ? 1u : 0u);
+      }
+    };
+    // P*V for k-steps [ks0, ks1) of the 128-key tile; A = P_t read from TMEM (it aliases S_t)
+    auto issue_pv = [&](int t, int buf, bool accumulate, int ks0, int ks1) {
+      const uint64_t vd = sdesc_at(hi_mnmajor, sKV + buf * T::kTileBytes);
+      const uint32_t d = tmem_base + T::kTmemO + t * kHeadDim;
+      const uint32_t a = tmem_base + T::kTmemS + t * kBlockN;
 #pragma unroll
-        for (int ks = ks0; ks < ks1; ++ks) {
-          mma_ts<kTF32>(d, a + ks * 8, vd + static_cast<uint32_t>(ks * (T::kUmmaK * 128 / 16)), idesc_pv,
-                        (accumulate || ks > 0) ? 1u : 0u);
+      for (int ks = ks0; ks < ks1; ++ks) {
+        mma_ts<kTF32>(d, a + ks * 8, vd + static_cast<uint32_t>(ks * (T::kUmmaK * 128 / 16)), idesc_pv,
+                      (accumulate || ks > 0) ? 1u : 0u);
+      }
+    };
+    int ring = 0;                 // K/V ring index, same sequence as the producer's
+    uint32_t p_par = 0;           // bit t: parity of the next bar_p[t] phase (one phase per K/V step of slot t, over all items)
+    uint32_t q_par = 0;           // bit qb: parity of the next bar_q[qb] phase (one phase per Q tile loaded into buffer qb)
+    uint32_t of_par = 0;          // bit t: parity of the next bar_ofree[t] phase
+    uint32_t of_pend = 0;         // bit t: an epilogue of the previous item is (or will be) reading TMEM and arrives on bar_ofree[t]
+    // The first P*V of an item overwrites O_t: every epilogue of the previous item that reads TMEM must be done with it.
+    // Arrivals are tied to work (a slot that had none does not arrive), so a slot can never arrive twice in one phase.
+    auto wait_ofree = [&]() {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (of_pend & (1u << t)) {
+          mbar_wait(bar_ofree + 8 * t, (of_par >> t) & 1u, TAG_O_FREE);
+          of_par ^= 1u << t;
         }
-      };
-      auto wait_full = [&](int i) { mbar_wait(bar_full + 8 * (i % T::kNBuf), (i / T::kNBuf) & 1, TAG_KV_FULL); };
-      // P_t(j) V -> O_t in two 64-key halves as the softmax warps deliver them, then (unless this was the slot's last
-      // K/V tile) S_t(j+1); the tensor pipe executes in issue order, so S_t(j+1) may overwrite the columns P_t(j) aliased.
-      auto step = [&](int t, int j, bool last, int qbuf, int vbuf, int kbuf, bool release) {
-#if FA_OPT_SPLITP
-        FA_TRACE_AT(2 + t, j, 0);
-        mbar_wait(bar_p + 16 * t, j & 1, TAG_P_FULL);          // keys [0, 64) of P are in TMEM
-        tc_fence_after();
-        FA_TRACE_AT(2 + t, j, 1);
-        if (elect_one_sync()) issue_pv(t, vbuf, j > 0, 0, kKStepsPV / 2);
-        __syncwarp();
-        FA_TRACE_AT(2 + t, j, 2);
+      }
+      if (of_pend) tc_fence_after();
+      of_pend = 0;
+    };
+#if FA_TRACE
+    int steps_a = 0, steps_b = 0;
 #endif
-        mbar_wait(bar_p + 16 * t + 8, j & 1, TAG_P_FULL);      // keys [64, 128)
-        tc_fence_after();
-        FA_TRACE_AT(2 + t, j, 3);
-        if (elect_one_sync()) {
-          issue_pv(t, vbuf, j > 0, FA_OPT_SPLITP ? kKStepsPV / 2 : 0, kKStepsPV);
-          if (release) tc_commit(bar_empty + 8 * vbuf);
-          if (last) {
-            tc_commit(bar_o + 8 * t);
-          } else {
-            issue_s(t, qbuf, kbuf);
-            tc_commit(bar_s + 8 * t);
-            if (release) tc_commit(bar_empty + 8 * kbuf);
-          }
+    auto wait_full = [&](int i) { mbar_wait(bar_full + 8 * (i % T::kNBuf), (i / T::kNBuf) & 1, TAG_KV_FULL); };
+    // P_t(j) V -> O_t in two 64-key halves as the softmax warps deliver them, then (unless this was the slot's last
+    // K/V tile of the item) S_t(j+1); the tensor pipe executes in issue order, so S_t(j+1) may overwrite the columns
+    // P_t(j) aliased.
+    auto step = [&](int t, int j, bool last, int qbuf, int vbuf, int kbuf, bool release) {
+      const uint32_t par = (p_par >> t) & 1u;
+      p_par ^= 1u << t;
+#if FA_TRACE
+      const int g = t == 0 ? steps_a++ : steps_b++;
+#endif
+#if FA_OPT_SPLITP
+      FA_TRACE_AT(2 + t, g, 0);
+      mbar_wait(bar_p + 16 * t, par, TAG_P_FULL);            // keys [0, 64) of P are in TMEM
+      tc_fence_after();
+      FA_TRACE_AT(2 + t, g, 1);
+      if (elect_one_sync()) issue_pv(t, vbuf, j > 0, 0, kKStepsPV / 2);
+      __syncwarp();
+      FA_TRACE_AT(2 + t, g, 2);
+#endif
+      mbar_wait(bar_p + 16 * t + 8, par, TAG_P_FULL);        // keys [64, 128)
+      tc_fence_after();
+      FA_TRACE_AT(2 + t, g, 3);
+      if (elect_one_sync()) {
+        issue_pv(t, vbuf, j > 0, FA_OPT_SPLITP ? kKStepsPV / 2 : 0, kKStepsPV);
+        if (release) tc_commit(bar_empty + 8 * vbuf);
+        if (last) {
+          tc_commit(bar_o + 8 * t);
+        } else {
+          issue_s(t, qbuf, kbuf);
+          tc_commit(bar_s + 8 * t);
+          if (release) tc_commit(bar_empty + 8 * kbuf);
         }
-        __syncwarp();
-        FA_TRACE_AT(2 + t, j, 6);
-      };
+      }
+      __syncwarp();
+      FA_TRACE_AT(2 + t, g, 6);
+    };
 
-      if (!split) {
-        // ---- two Q tiles share every K/V tile: ring index of K_j is 2j, of V_j is 2j+1 ----
-        if (n_tile[0] > 0) mbar_wait(bar_q, 0, TAG_Q_FULL);
-        if (n_tile[1] > 0) mbar_wait(bar_q + 8, 0, TAG_Q_FULL);
-        FA_TRACE_MISC(2, 1);
-        wait_full(0);
+    for (int seq = 0;; ++seq) {
+      const int item = next_item(seq);
+      if (item < 0) break;
+      const Item w = decode_item<kCausal>(p, item);
+      if (w.n_max == 0) continue;
+      const int set = seq % kQS;
+      // Q tiles of this item
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (w.n(t) > 0 && !(w.split && t == 1)) {
+          const int qb = set * 2 + t;
+          mbar_wait(bar_q + 8 * qb, (q_par >> qb) & 1u, TAG_Q_FULL);
+          q_par ^= 1u << qb;
+        }
+      }
+      if (seq == 0) FA_TRACE_MISC(2, 1);
+      if (!w.split) {
+        // ---- two Q tiles share every K/V tile: K_j then V_j in ring order ----
+        const int r0 = ring;
+        ring += 2 * w.n_max;
+        wait_full(r0);
         tc_fence_after();
-        FA_TRACE_MISC(2, 2);
+        if (seq == 0) FA_TRACE_MISC(2, 2);
         if (elect_one_sync()) {
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            if (n_tile[t] > 0) {
-              issue_s(t, t, 0);
+            if (w.n(t) > 0) {
+              issue_s(t, set * 2 + t, r0 % T::kNBuf);
               tc_commit(bar_s + 8 * t);
             }
           }
-          tc_commit(bar_empty + 0);
+          tc_commit(bar_empty + 8 * (r0 % T::kNBuf));
         }
         __syncwarp();
-        FA_TRACE_MISC(2, 3);
-        for (int j = 0; j < n_max; ++j) {
-          const int iv = 2 * j + 1, ik = 2 * j + 2;
+        if (seq == 0) FA_TRACE_MISC(2, 3);
+        wait_ofree();
+        for (int j = 0; j < w.n_max; ++j) {
+          const int iv = r0 + 2 * j + 1, ik = r0 + 2 * j + 2;
           const int vbuf = iv % T::kNBuf, kbuf = ik % T::kNBuf;
           wait_full(iv);
-          if (j + 1 < n_max) wait_full(ik);
+          if (j + 1 < w.n_max) wait_full(ik);
           tc_fence_after();
 #pragma unroll
           for (int t = 0; t < 2; ++t)
-            if (j < n_tile[t]) step(t, j, j == n_tile[t] - 1, t, vbuf, kbuf, false);
+            if (j < w.n(t)) step(t, j, j == w.n(t) - 1, set * 2 + t, vbuf, kbuf, false);
           if (elect_one_sync()) {
             tc_commit(bar_empty + 8 * vbuf);
-            if (j + 1 < n_max) tc_commit(bar_empty + 8 * kbuf);
+            if (j + 1 < w.n_max) tc_commit(bar_empty + 8 * kbuf);
           }
           __syncwarp();
         }
       } else {
         // ---- split-KV: each slot has its own K/V tiles; ring order K_A0, K_B0, then V_A(j), K_A(j+1), V_B(j), K_B(j+1) ----
-        mbar_wait(bar_q, 0, TAG_Q_FULL);
-        wait_full(0);
-        if (n_tile[1] > 0) wait_full(1);
+        const int qb = set * 2;
+        const int ia = ring++;
+        const int ib = w.n1 > 0 ? ring++ : ia;
+        wait_full(ia);
+        if (w.n1 > 0) wait_full(ib);
         tc_fence_after();
         if (elect_one_sync()) {
-          issue_s(0, 0, 0);
+          issue_s(0, qb, ia % T::kNBuf);
           tc_commit(bar_s);
-          tc_commit(bar_empty);
-          if (n_tile[1] > 0) {
-            issue_s(1, 0, 1);
+          tc_commit(bar_empty + 8 * (ia % T::kNBuf));
+          if (w.n1 > 0) {
+            issue_s(1, qb, ib % T::kNBuf);
             tc_commit(bar_s + 8);
-            tc_commit(bar_empty + 8);
+            tc_commit(bar_empty + 8 * (ib % T::kNBuf));
           }
         }
         __syncwarp();
-        int ring = n_tile[1] > 0 ? 2 : 1;
-        for (int j = 0; j < n_max; ++j) {
+        wait_ofree();
+        for (int j = 0; j < w.n_max; ++j) {
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            if (j < n_tile[t]) {
-              const bool last = (j == n_tile[t] - 1);
+            if (j < w.n(t)) {
+              const bool last = (j == w.n(t) - 1);
               const int iv = ring++;
               const int ik = last ? iv : ring++;
               wait_full(iv);
               if (!last) wait_full(ik);
               tc_fence_after();
-              step(t, j, last, 0, iv % T::kNBuf, ik % T::kNBuf, true);
+              step(t, j, last, qb, iv % T::kNBuf, ik % T::kNBuf, true);
             }
           }
         }
       }
+      // who will read TMEM in this item's epilogue: both slots of a 256-row item that had work; slot A alone (its own
+      // accumulator and, for the merge, slot B's) in a 128-row item
+      of_pend = w.single ? 1u : ((w.n0 > 0 ? 1u : 0u) | (w.n1 > 0 ? 2u : 0u));
     }
   } else {
     // =========================== softmax + epilogue (warps 0-7) ===========================
     const int t = warp >> 2;                       // tile slot of this warpgroup
     const int r = (warp & 3) * 32 + lane;          // row within the tile == TMEM lane
-    const int q_row = (t == 0 ? row0 : row_of_tile1) + r;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t tS = tmem_base + lane_base + T::kTmemS + t * kBlockN;
     const uint32_t tO = tmem_base + lane_base + T::kTmemO + t * kHeadDim;
-    const int n_mine = n_tile[t];
+    const uint32_t tO_other = tmem_base + lane_base + T::kTmemO + (t ^ 1) * kHeadDim;
     const float c = p.scale_log2;
-
-    float m = -INFINITY;  // running (possibly stale) row max, in raw q.k units
-    float l = 0.f;        // running row sum of exp2((s - m) * c)
-
     const bool tracer = (warp & 3) == 0 && lane == 0;
     (void)tracer;
-    for (int j = 0; j < n_mine; ++j) {
-      if (tracer) FA_TRACE_AT(t, j, 0);
-      mbar_wait(bar_s + 8 * t, j & 1, TAG_S_FULL);
-      tc_fence_after();
-      if (tracer) FA_TRACE_AT(t, j, 1);
-      float s[128];
-      // masking: key kv0 + i is visible iff i <= limit
-      const int kv0 = (kv_first[t] + j) * kBlockN;
-      int limit = p.n_k - 1 - kv0;
-      if (kCausal) limit = min(limit, q_row + p.causal_offset - kv0);
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#if FA_OPT_LDPIPE
-      // chunk q's row-max pass runs while chunk q+1 is still in flight from TMEM
-      tmem_ld32(tS, reinterpret_cast<uint32_t*>(&s[0]));
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        tc_wait_ld();
-        if (q4 < 3) tmem_ld32(tS + (q4 + 1) * 32, reinterpret_cast<uint32_t*>(&s[(q4 + 1) * 32]));
-        if (limit < kBlockN - 1) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (q4 * 32 + i > limit) s[q4 * 32 + i] = -INFINITY;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          mx0 = fmaxf(mx0, s[q4 * 32 + i]);
-          mx1 = fmaxf(mx1, s[q4 * 32 + i + 1]);
-          mx2 = fmaxf(mx2, s[q4 * 32 + i + 2]);
-          mx3 = fmaxf(mx3, s[q4 * 32 + i + 3]);
-        }
-      }
-#else
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) tmem_ld32(tS + q4 * 32, reinterpret_cast<uint32_t*>(&s[q4 * 32]));
-      tc_wait_ld();
-      if (limit < kBlockN - 1) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i > limit) s[i] = -INFINITY;
-      }
-#pragma unroll
-      for (int i = 0; i < 128; i += 4) {
-        mx0 = fmaxf(mx0, s[i]);
-        mx1 = fmaxf(mx1, s[i + 1]);
-        mx2 = fmaxf(mx2, s[i + 2]);
-        mx3 = fmaxf(mx3, s[i + 3]);
-      }
-#endif
-      const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
-      if (tracer) FA_TRACE_AT(t, j, 2);
+    int steps = 0;            // K/V steps of this slot so far, over all items (parity of bar_s / bar_p)
+    uint32_t o_par = 0;       // bit u: parity of the next bar_o[u] phase (one phase per item in which slot u has work)
 
-      if (j == 0) {
-        m = m_new;
-      } else {
-        // lazy rescale: only move the reference max when it grew by more than 2^kRescaleThreshold
-        const bool need = (m_new - m) * c > kRescaleThreshold;   // (-inf -> finite) gives +inf -> true
-        if (__any_sync(0xffffffffu, need)) {
-          const float m_use = need ? m_new : m;
-          const float alpha = need ? ex2((m - m_use) * c) : 1.0f;  // m = -inf -> 0
-          l *= alpha;
+    // exp2 of keys [i0, i0 + 32) of the S row held in s[], in place, with the partial row sums in l0..l3
+    auto exp_chunk = [&](float* s, const int i0, const float neg_mc, float& l0, float& l1, float& l2, float& l3) {
 #pragma unroll
-          for (int cc = 0; cc < kHeadDim / 16; ++cc) {
-            uint32_t o[16];
-            tmem_ld16(tO + cc * 16, o);
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tO + cc * 16, o);
-          }
-          m = m_use;
-        }
-      }
-      const float m_safe = (m == -INFINITY) ? 0.f : m;
-      const float neg_mc = -m_safe * c;
-      // P = exp2(s*c - m*c) in two 64-key halves; each half is written to TMEM and handed to the MMA thread as soon
-      // as it is complete, so the first half of P*V runs under the second half of the exps.
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-#pragma unroll
-        for (int i = h * 64; i < h * 64 + 64; i += 4) {
-          // which of these 4 elements take the polynomial route: the first FA_OPT_POLY/2 pairs of every 8 elements
-          const bool kPoly01 = (FA_OPT_POLY >= 2) && ((i & 4) == 0);
-          const bool kPoly23 = (FA_OPT_POLY >= 4) && ((i & 4) == 0);
+      for (int i = i0; i < i0 + 32; i += 4) {
+        // which of these 4 elements take the polynomial route: the first FA_OPT_POLY/2 pairs of every 8 elements
+        const bool kPoly01 = (FA_OPT_POLY >= 2) && ((i & 4) == 0);
+        const bool kPoly23 = (FA_OPT_POLY >= 4) && ((i & 4) == 0);
+        bool packed = false;
 #if FA_OPT_F2
-          if constexpr (!kTF32) {
+        if constexpr (!kTF32) {
+          packed = true;
           float2 a01 = ffma2(make_float2(s[i], s[i + 1]), make_float2(c, c), make_float2(neg_mc, neg_mc));
           float2 a23 = ffma2(make_float2(s[i + 2], s[i + 3]), make_float2(c, c), make_float2(neg_mc, neg_mc));
           if (kPoly01) {
@@ -523,9 +584,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             s[i + 2] = ex2(a23.x);
             s[i + 3] = ex2(a23.y);
           }
-          } else
+          const float2 s01 = fadd2(make_float2(l0, l1), make_float2(s[i], s[i + 1]));
+          const float2 s23 = fadd2(make_float2(l2, l3), make_float2(s[i + 2], s[i + 3]));
+          l0 = s01.x; l1 = s01.y; l2 = s23.x; l3 = s23.y;
+        }
 #endif
-          {
+        if (!packed) {
           if (kPoly01) {
             s[i] = exp2_poly(fmaf(s[i], c, neg_mc));
             s[i + 1] = exp2_poly(fmaf(s[i + 1], c, neg_mc));
@@ -540,7 +604,6 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             s[i + 2] = ex2(fmaf(s[i + 2], c, neg_mc));
             s[i + 3] = ex2(fmaf(s[i + 3], c, neg_mc));
           }
-          }
           if constexpr (kTF32) {
             // kind::tf32 reads only the top 19 bits of P; sum exactly those values so that O = (sum P~ V) / (sum P~)
             // is normalised by what the tensor core actually multiplied (removes the truncation bias from O)
@@ -549,166 +612,240 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             s[i + 2] = __uint_as_float(__float_as_uint(s[i + 2]) & 0xFFFFE000u);
             s[i + 3] = __uint_as_float(__float_as_uint(s[i + 3]) & 0xFFFFE000u);
           }
-#if FA_OPT_F2
-          if constexpr (!kTF32) {
-          const float2 s01 = fadd2(make_float2(l0, l1), make_float2(s[i], s[i + 1]));
-          const float2 s23 = fadd2(make_float2(l2, l3), make_float2(s[i + 2], s[i + 3]));
-          l0 = s01.x; l1 = s01.y; l2 = s23.x; l3 = s23.y;
-          } else
-#endif
-          {
           l0 += s[i];
           l1 += s[i + 1];
           l2 += s[i + 2];
           l3 += s[i + 3];
+        }
+      }
+    };
+
+    for (int seq = 0;; ++seq) {
+      const int item = next_item(seq);
+      if (item < 0) break;
+      const Item w = decode_item<kCausal>(p, item);
+      const int set = seq % kQS;
+      const int n_mine = w.n(t);
+      const int q_row = (t == 0 ? w.row0 : w.row1) + r;
+      const int kv_first = t == 0 ? 0 : w.kv_first1;
+
+      float m = -INFINITY;  // running (possibly stale) row max, in raw q.k units
+      float l = 0.f;        // running row sum of exp2((s - m) * c)
+
+      for (int j = 0; j < n_mine; ++j) {
+        const int g = steps++;
+        if (tracer) FA_TRACE_AT(t, g, 0);
+        mbar_wait(bar_s + 8 * t, g & 1, TAG_S_FULL);
+        tc_fence_after();
+        if (tracer) FA_TRACE_AT(t, g, 1);
+        float s[128];
+        // masking: key kv0 + i is visible iff i <= limit
+        const int kv0 = (kv_first + j) * kBlockN;
+        int limit = p.n_k - 1 - kv0;
+        if (kCausal) limit = min(limit, q_row + p.causal_offset - kv0);
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) tmem_ld32(tS + q4 * 32, reinterpret_cast<uint32_t*>(&s[q4 * 32]));
+        tc_wait_ld();
+        if (limit < kBlockN - 1) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i > limit) s[i] = -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          mx0 = fmaxf(mx0, s[i]);
+          mx1 = fmaxf(mx1, s[i + 1]);
+          mx2 = fmaxf(mx2, s[i + 2]);
+          mx3 = fmaxf(mx3, s[i + 3]);
+        }
+        const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+        if (tracer) FA_TRACE_AT(t, g, 2);
+
+        if (j == 0) {
+          m = m_new;
+        } else {
+          // lazy rescale: only move the reference max when it grew by more than 2^kRescaleThreshold
+          const bool need = (m_new - m) * c > kRescaleThreshold;   // (-inf -> finite) gives +inf -> true
+          if (__any_sync(0xffffffffu, need)) {
+            const float m_use = need ? m_new : m;
+            const float alpha = need ? ex2((m - m_use) * c) : 1.0f;  // m = -inf -> 0
+            l *= alpha;
+#pragma unroll
+            for (int cc = 0; cc < kHeadDim / 16; ++cc) {
+              uint32_t o[16];
+              tmem_ld16(tO + cc * 16, o);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(tO + cc * 16, o);
+            }
+            m = m_use;
           }
         }
-        if constexpr (kTF32) {
-          tmem_st32(tS + h * 64, reinterpret_cast<uint32_t*>(&s[h * 64]));
-          tmem_st32(tS + h * 64 + 32, reinterpret_cast<uint32_t*>(&s[h * 64 + 32]));
-        } else {
-          uint32_t pk[32];
+        const float m_safe = (m == -INFINITY) ? 0.f : m;
+        const float neg_mc = -m_safe * c;
+        // P = exp2(s*c - m*c) in two 64-key halves; each half is written to TMEM and handed to the MMA warp as soon
+        // as it is complete, so the first half of P*V runs under the second half of the exps.
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(s[h * 64 + 2 * i], s[h * 64 + 2 * i + 1]);
-          tmem_st32(tS + h * 32, &pk[0]);
-        }
+        for (int h = 0; h < 2; ++h) {
+          exp_chunk(s, h * 64, neg_mc, l0, l1, l2, l3);
+          exp_chunk(s, h * 64 + 32, neg_mc, l0, l1, l2, l3);
+          if constexpr (kTF32) {
+            tmem_st32(tS + h * 64, reinterpret_cast<uint32_t*>(&s[h * 64]));
+            tmem_st32(tS + h * 64 + 32, reinterpret_cast<uint32_t*>(&s[h * 64 + 32]));
+          } else {
+            uint32_t pk[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(s[h * 64 + 2 * i], s[h * 64 + 2 * i + 1]);
+            tmem_st32(tS + h * 32, &pk[0]);
+          }
 #if FA_OPT_SPLITP
-        if (tracer) FA_TRACE_AT(t, j, 3 + 2 * h);
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(bar_p + 16 * t + 8 * h);
-        if (tracer) FA_TRACE_AT(t, j, 4 + 2 * h);
-#else
-        if (h == 1) {
-          if (tracer) FA_TRACE_AT(t, j, 5);
+          if (tracer) FA_TRACE_AT(t, g, 3 + 2 * h);
           tc_wait_st();
           tc_fence_before();
-          mbar_arrive(bar_p + 16 * t + 8);
-          if (tracer) FA_TRACE_AT(t, j, 6);
-        }
+          mbar_arrive(bar_p + 16 * t + 8 * h);
+          if (tracer) FA_TRACE_AT(t, g, 4 + 2 * h);
+#else
+          if (h == 1) {
+            if (tracer) FA_TRACE_AT(t, g, 5);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_p + 16 * t + 8);
+            if (tracer) FA_TRACE_AT(t, g, 6);
+          }
 #endif
-      }
-      l += (l0 + l1) + (l2 + l3);
-    }
-
-    // ---- epilogue: O/l -> swizzled SMEM (reusing this tile's Q buffer) -> TMA store; LSE -> global ----
-    if (tracer) FA_TRACE_MISC(t, 2);
-    if (n_mine > 0) {
-      mbar_wait(bar_o + 8 * t, 0, TAG_O_FINAL);
-      tc_fence_after();
-    }
-    if (tracer) FA_TRACE_MISC(t, 3);
-    // scale of this slot's accumulator and of the partner's partial (split-KV tail CTAs only) in the final O
-    float f_self = (n_mine > 0 && l > 0.f) ? 1.0f / l : 0.f;
-    float f_other = 0.f;
-    float lse_val = -INFINITY;
-    {
-      const float m_safe = (m == -INFINITY) ? 0.f : m;
-      if (n_mine > 0 && l > 0.f) lse_val = m_safe * p.scale + logf(l);
-    }
-    // split-KV exchange area: the K/V ring is dead once both slots' last MMAs have retired.
-    // xO[col][row] fp32 (column-major: a warp's 32 rows are 32 consecutive words -> conflict-free), then m[128], l[128]
-    const uint32_t xO = sKV;
-    const uint32_t xML = sKV + kHeadDim * kBlockM * 4;
-    bool stores = !(single_tile && t == 1);        // slot B of a 128-row CTA owns no output rows
-    // both accumulators final => every tcgen05.mma that read the ring has retired
-    if (split && n_tile[t ^ 1] > 0) mbar_wait(bar_o + 8 * (t ^ 1), 0, TAG_O_FINAL);
-    if (split && n_tile[1] > 0) {
-      tc_fence_after();
-      if (t == 1) {
-#pragma unroll
-        for (int cc = 0; cc < kHeadDim / 32; ++cc) {
-          uint32_t o[32];
-          tmem_ld32(tO + cc * 32, o);
-          tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) st_shared_b32(xO + ((cc * 32 + i) * kBlockM + r) * 4, o[i]);
         }
-        st_shared_b32(xML + r * 4, __float_as_uint(m));
-        st_shared_b32(xML + (kBlockM + r) * 4, __float_as_uint(l));
-        named_bar_arrive(kBarMerge, 256);
-      } else {
-        named_bar_sync(kBarMerge, 256);
-        const float m_b = __uint_as_float(ld_shared_b32(xML + r * 4));
-        const float l_b = __uint_as_float(ld_shared_b32(xML + (kBlockM + r) * 4));
-        // log-sum-exp merge of (O_A, m, l) and (O_B, m_b, l_b); both maxima are in raw q.k units, sums in the exp2 domain
-        const float m_all = fmaxf(m, m_b);
-        const float a_a = (m == -INFINITY) ? 0.f : ex2((m - m_all) * c);
-        const float a_b = (m_b == -INFINITY) ? 0.f : ex2((m_b - m_all) * c);
-        const float l_all = l * a_a + l_b * a_b;
-        const float inv = l_all > 0.f ? 1.0f / l_all : 0.f;
-        f_self = a_a * inv;
-        f_other = a_b * inv;
-        lse_val = l_all > 0.f ? m_all * p.scale + logf(l_all) : -INFINITY;
+        l += (l0 + l1) + (l2 + l3);
       }
-    }
-    if (p.lse != nullptr && stores && q_row < p.n_q)
-      p.lse[(static_cast<int64_t>(batch) * p.heads + head) * p.n_q + q_row] = lse_val;
-    const uint32_t stage = sQ + t * T::kTileBytes;       // kDChunks boxes of 16 KB
-    const uint32_t row_off = r * 128;
-    const uint32_t sw = r & 7;
-    constexpr int kRounds = T::kOChunks / T::kDChunks;   // 1, or 2 for bf16-in / fp32-out
-    constexpr int kColsPerChunk = T::kOutElemsPerChunk;  // 32 (fp32) or 64 (bf16)
-    if (stores) {
+
+      // ---- epilogue: O/l -> swizzled SMEM (reusing this slot's Q buffer) -> TMA store; LSE -> global ----
+      if (tracer && seq == 0) FA_TRACE_MISC(t, 2);
 #pragma unroll
-    for (int round = 0; round < kRounds; ++round) {
+      for (int u = 0; u < 2; ++u) {
+        // own accumulator final; in split mode slot A also needs the partner's (it merges O_B).  A completion that is
+        // not waited for here still happens: keep its parity count in step.
+        if (w.n(u) > 0) {
+          if (u == t || (w.split && t == 0)) mbar_wait(bar_o + 8 * u, (o_par >> u) & 1u, TAG_O_FINAL);
+          o_par ^= 1u << u;
+        }
+      }
+      tc_fence_after();
+      if (tracer && seq == 0) FA_TRACE_MISC(t, 3);
+      // scale of this slot's accumulator and of the partner's partial (split-KV tail items only) in the final O
+      float f_self = (n_mine > 0 && l > 0.f) ? 1.0f / l : 0.f;
+      float f_other = 0.f;
+      float lse_val = -INFINITY;
+      {
+        const float m_safe = (m == -INFINITY) ? 0.f : m;
+        if (n_mine > 0 && l > 0.f) lse_val = m_safe * p.scale + logf(l);
+      }
+      const bool stores = !(w.single && t == 1);        // slot B of a 128-row item owns no output rows
+      const bool merge = w.split && w.n1 > 0;
+      if (merge) {
+        if (t == 1) {
+          st_shared_b32(s_ml + r * 4, __float_as_uint(m));
+          st_shared_b32(s_ml + (kBlockM + r) * 4, __float_as_uint(l));
+          named_bar_arrive(kBarMerge, 256);
+        } else {
+          named_bar_sync(kBarMerge, 256);
+          const float m_b = __uint_as_float(ld_shared_b32(s_ml + r * 4));
+          const float l_b = __uint_as_float(ld_shared_b32(s_ml + (kBlockM + r) * 4));
+          // log-sum-exp merge of (O_A, m, l) and (O_B, m_b, l_b); both maxima are in raw q.k units, sums in the exp2 domain
+          const float m_all = fmaxf(m, m_b);
+          const float a_a = (m == -INFINITY) ? 0.f : ex2((m - m_all) * c);
+          const float a_b = (m_b == -INFINITY) ? 0.f : ex2((m_b - m_all) * c);
+          const float l_all = l * a_a + l_b * a_b;
+          const float inv = l_all > 0.f ? 1.0f / l_all : 0.f;
+          f_self = a_a * inv;
+          f_other = a_b * inv;
+          lse_val = l_all > 0.f ? m_all * p.scale + logf(l_all) : -INFINITY;
+        }
+      }
+      const uint32_t stage = sQ + (set * 2 + t) * T::kTileBytes;   // kDChunks boxes of 16 KB
+      const uint32_t row_off = r * 128;
+      const uint32_t sw = r & 7;
+      constexpr int kRounds = T::kOChunks / T::kDChunks;   // 1, or 2 for bf16-in / fp32-out
+      constexpr int kColsPerChunk = T::kOutElemsPerChunk;  // 32 (fp32) or 64 (bf16)
+      constexpr int kLastCol0 = (kRounds * T::kDChunks - 1) * kColsPerChunk + (kColsPerChunk / 32 - 1) * 32;
+      if (!stores) {
+        // slot B of a 128-row item: nothing to read from TMEM (slot A merges O_B) and no output rows; its Q buffer was unused
+        if ((warp & 3) == 0 && lane == 0) mbar_arrive(bar_qfree + 8 * (set * 2 + t));
+      } else {
 #pragma unroll
-      for (int ch = 0; ch < T::kDChunks; ++ch) {
-        const int col0 = (round * T::kDChunks + ch) * kColsPerChunk;
+        for (int round = 0; round < kRounds; ++round) {
 #pragma unroll
-        for (int half = 0; half < kColsPerChunk / 32; ++half) {
-          uint32_t o[32];
-          if (n_mine > 0) {
-            tmem_ld32(tO + col0 + half * 32, o);
-            tc_wait_ld();
-          } else {
+          for (int ch = 0; ch < T::kDChunks; ++ch) {
+            const int col0 = (round * T::kDChunks + ch) * kColsPerChunk;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = 0u;
-          }
+            for (int half = 0; half < kColsPerChunk / 32; ++half) {
+              const int cbase = col0 + half * 32;
+              uint32_t o[32];
+              if (n_mine > 0) {
+                tmem_ld32(tO + cbase, o);
+                tc_wait_ld();
+              } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f_self);
-          if (split && n_tile[1] > 0) {
+                for (int i = 0; i < 32; ++i) o[i] = 0u;
+              }
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              o[i] = __float_as_uint(fmaf(__uint_as_float(ld_shared_b32(xO + ((col0 + half * 32 + i) * kBlockM + r) * 4)), f_other,
-                                          __uint_as_float(o[i])));
-          }
-          const uint32_t base = stage + ch * kChunkBytes + row_off;
-          if constexpr (T::kOutSize == 4) {
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f_self);
+              if (merge) {
+                uint32_t ob[32];
+                tmem_ld32(tO_other + cbase, ob);
+                tc_wait_ld();
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-              st_shared_v4(base + ((static_cast<uint32_t>(g) ^ sw) << 4), o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
-          } else {
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(fmaf(__uint_as_float(ob[i]), f_other, __uint_as_float(o[i])));
+              }
+              if (cbase == kLastCol0 && n_mine > 0) {
+                // last TMEM read of this item: the MMA warp may overwrite O_t (and O_B after a merge) with the next item's
+                // first P*V.  Slots without work read nothing and do not arrive (see wait_ofree in the MMA warp).
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_ofree + 8 * t);
+              }
+              const uint32_t base = stage + ch * kChunkBytes + row_off;
+              if constexpr (T::kOutSize == 4) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t chunk16 = static_cast<uint32_t>(half * 4 + g);
-              st_shared_v4(base + ((chunk16 ^ sw) << 4),
-                           pack_bf16x2(__uint_as_float(o[8 * g]), __uint_as_float(o[8 * g + 1])),
-                           pack_bf16x2(__uint_as_float(o[8 * g + 2]), __uint_as_float(o[8 * g + 3])),
-                           pack_bf16x2(__uint_as_float(o[8 * g + 4]), __uint_as_float(o[8 * g + 5])),
-                           pack_bf16x2(__uint_as_float(o[8 * g + 6]), __uint_as_float(o[8 * g + 7])));
+                for (int g = 0; g < 8; ++g)
+                  st_shared_v4(base + ((static_cast<uint32_t>(g) ^ sw) << 4), o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+              } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  const uint32_t chunk16 = static_cast<uint32_t>(half * 4 + g);
+                  st_shared_v4(base + ((chunk16 ^ sw) << 4),
+                               pack_bf16x2(__uint_as_float(o[8 * g]), __uint_as_float(o[8 * g + 1])),
+                               pack_bf16x2(__uint_as_float(o[8 * g + 2]), __uint_as_float(o[8 * g + 3])),
+                               pack_bf16x2(__uint_as_float(o[8 * g + 4]), __uint_as_float(o[8 * g + 5])),
+                               pack_bf16x2(__uint_as_float(o[8 * g + 6]), __uint_as_float(o[8 * g + 7])));
+                }
+              }
             }
           }
-        }
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1 + t, 128);
-      if (tracer) FA_TRACE_MISC(t, 4);
-      if ((warp & 3) == 0 && lane == 0) {
+          fence_proxy_async_smem();
+          named_bar_sync(1 + t, 128);
+          if (tracer && seq == 0) FA_TRACE_MISC(t, 4);
+          if ((warp & 3) == 0 && lane == 0) {
 #pragma unroll
-        for (int ch = 0; ch < T::kDChunks; ++ch)
-          tma_store_4d(&tm_o, stage + ch * kChunkBytes, (round * T::kDChunks + ch) * kColsPerChunk, row0 + t * kBlockM, head,
-                       batch);
-        tma_store_commit();
-        tma_store_wait_read();
-        FA_TRACE_MISC(t, 5);
+            for (int ch = 0; ch < T::kDChunks; ++ch)
+              tma_store_4d(&tm_o, stage + ch * kChunkBytes, (round * T::kDChunks + ch) * kColsPerChunk, w.row0 + t * kBlockM,
+                           w.head, w.batch);
+            tma_store_commit();
+            tma_store_wait_read();
+            if (seq == 0) FA_TRACE_MISC(t, 5);
+            if (round + 1 == kRounds) mbar_arrive(bar_qfree + 8 * (set * 2 + t));   // staging buffer read out: Q may land here again
+          }
+          if (round + 1 < kRounds) named_bar_sync(1 + t, 128);
+        }
+        // after the staging stores: a global store ahead of fence.proxy.async would make that fence wait for it
+        if (p.lse != nullptr && q_row < p.n_q)
+          p.lse[(static_cast<int64_t>(w.batch) * p.heads + w.head) * p.n_q + q_row] = lse_val;
       }
-      if (round + 1 < kRounds) named_bar_sync(1 + t, 128);
     }
     if ((warp & 3) == 0 && lane == 0) {
       tma_store_wait_all();
       FA_TRACE_MISC(t, 6);
-    }
     }
   }
 
@@ -718,6 +855,16 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (warp == 8) {
     __syncwarp();
     tmem_dealloc(tmem_base, 512);
+  }
+  if (p.work_counter != nullptr && threadIdx.x == 0) {
+    // the last CTA to finish re-arms the counters for the next launch that uses them
+    __threadfence();
+    const unsigned int done = atomicAdd(p.work_counter + 1, 1u);
+    if (done == gridDim.x - 1) {
+      p.work_counter[0] = 0u;
+      p.work_counter[1] = 0u;
+      __threadfence();
+    }
   }
 }
 

@@ -15,6 +15,8 @@ namespace fa {
 // which surfaces as a CUDA error on the host instead of a hung GPU.
 // ----------------------------------------------------------------------------------------------
 __device__ unsigned int g_fa_watchdog[4];  // [0]=tag, [1]=blockIdx.x, [2]=threadIdx.x, [3]=parity
+// optional copy in host-mapped pinned memory (set by the host side): still readable after the trap has killed the context
+__device__ unsigned int* g_fa_watchdog_host = nullptr;
 
 #ifndef FA_WATCHDOG_SPINS
 #define FA_WATCHDOG_SPINS (1u << 22)
@@ -57,6 +59,12 @@ FA_DEVINL void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag) {
       g_fa_watchdog[1] = blockIdx.x;
       g_fa_watchdog[2] = threadIdx.x;
       g_fa_watchdog[3] = parity;
+      unsigned int* wh = g_fa_watchdog_host;
+      if (wh != nullptr && atomicCAS(wh, 0u, tag) == 0u) {   // first expiry wins
+        wh[1] = blockIdx.x;
+        wh[2] = threadIdx.x;
+        wh[3] = parity;
+      }
       __threadfence_system();
       __trap();
     }

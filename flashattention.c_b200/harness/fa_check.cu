@@ -20,7 +20,10 @@
   do {                                                                               \
     cudaError_t e = (x);                                                             \
     if (e != cudaSuccess) {                                                          \
-      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); \
+      uint32_t wd__[4] = {0, 0, 0, 0};                                               \
+      fa_watchdog_info(wd__);                                                        \
+      printf("CUDA error %s at %s:%d (watchdog tag %u block %u thread %u parity %u)\n", cudaGetErrorString(e), __FILE__, __LINE__, \
+             wd__[0], wd__[1], wd__[2], wd__[3]);                                   \
       return 2;                                                                      \
     }                                                                                \
   } while (0)
@@ -91,7 +94,12 @@ int main(int argc, char** argv) {
   int rc = fa_forward_ex(&p, nullptr);
   if (rc) { printf("tcgen05 launch failed: %s %s\n", fa_strerror(rc), fa_last_cuda_error()); return 3; }
   cudaError_t e = cudaDeviceSynchronize();
-  if (e != cudaSuccess) { printf("tcgen05 kernel failed: %s\n", cudaGetErrorString(e)); return 3; }
+  if (e != cudaSuccess) {
+    uint32_t wd[4] = {0, 0, 0, 0};
+    fa_watchdog_info(wd);
+    printf("tcgen05 kernel failed: %s (watchdog tag %u block %u thread %u parity %u)\n", cudaGetErrorString(e), wd[0], wd[1], wd[2], wd[3]);
+    return 3;
+  }
 
   auto download = [&](void* dptr, std::vector<float>& h) -> int {
     h.resize(n_el);
@@ -177,7 +185,12 @@ int main(int argc, char** argv) {
     CK(cudaEventRecord(e0, nullptr));
     fa_forward_ex(&p, nullptr);
     CK(cudaEventRecord(e1, nullptr));
-    CK(cudaEventSynchronize(e1));
+    if (cudaEventSynchronize(e1) != cudaSuccess) {
+      uint32_t wd[4] = {0, 0, 0, 0};
+      fa_watchdog_info(wd);
+      printf("timed launch %d failed (watchdog tag %u block %u thread %u parity %u)\n", i, wd[0], wd[1], wd[2], wd[3]);
+      return 3;
+    }
     CK(cudaEventElapsedTime(&ms[i], e0, e1));
   }
   std::sort(ms.begin(), ms.end());

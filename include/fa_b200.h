@@ -134,6 +134,10 @@ const char* fa_last_cuda_error(void); /* text of the last CUDA failure seen by t
 int fa_last_impl(void);               /* enum fa_impl of the last successful launch on this thread */
 int fa_version(void);
 int64_t fa_launch_count(void);        /* number of kernels this library has launched in this process */
+/* Every mbarrier wait in the kernels is bounded; on expiry the CTA records where it was stuck and traps, so a pipeline
+ * bug surfaces as a CUDA error instead of a hung GPU.  out = {barrier tag (0 = never expired), blockIdx.x, threadIdx.x,
+ * phase parity} of the first expiry in this process (kept in host-mapped memory, readable after the failed launch). */
+int fa_watchdog_info(uint32_t out[4]);
 
 #ifdef __cplusplus
 }
