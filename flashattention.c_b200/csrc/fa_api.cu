@@ -483,15 +483,48 @@ int fa_forward_host(const void* qh, const void* kh, const void* vh, void* oh, in
   }
   // Every (batch, head) is independent, so the copy-in, the kernel and the copy-out are pipelined over chunks of
   // the flattened batch*heads axis on three streams: H2D of chunk g+1 and D2H of chunk g-1 overlap the kernel of g.
+  // The job is bound by the H2D copies (3/4 of the bytes), which run back to back; what is left to shorten is the tail
+  // after the last H2D — the last chunk's kernel and D2H — so the chunks shrink geometrically towards the end
+  // (each chunk = kDecay of what remains, at least kMinChunkBytes of traffic and at least one head).
   const int64_t bh = batch * heads;
-  // chunk size ~32 MB of traffic (measured on B200/PCIe5, C2: 1 chunk 2.94 ms, 2: 2.48, 4: 2.29, 8: 2.46, 16: 2.56)
-  int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(bh, kHostMaxChunks), (int64_t)((2 * bq + 2 * bkv + (16u << 20)) >> 25)));
-  if (const char* e = getenv("FA_B200_HOST_CHUNKS")) chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(bh, kHostMaxChunks), atoi(e)));
-  const int64_t per = (bh + chunks - 1) / chunks;
   const size_t row_q = (size_t)n_q * head_dim * es, row_kv = (size_t)n_k * head_dim * es;
-  int g = 0;
-  for (int64_t h0 = 0; h0 < bh; h0 += per, ++g) {
-    const int64_t nh = std::min<int64_t>(per, bh - h0);
+  int64_t sched[kHostMaxChunks];
+  int chunks = 0;
+  {
+    double decay = 0.4;
+    if (const char* e = getenv("FA_B200_HOST_DECAY")) decay = std::min(1.0, std::max(0.05, atof(e)));
+    const size_t head_bytes = 2 * row_q + 2 * row_kv;
+    const int64_t min_heads = std::max<int64_t>(1, (int64_t)(((size_t)2 << 20) + head_bytes - 1) / (int64_t)head_bytes);
+    int64_t left = bh;
+    while (left > 0) {
+      int64_t take = chunks + 1 == kHostMaxChunks ? left : std::max<int64_t>(min_heads, (int64_t)std::ceil(left * decay));
+      take = std::min(take, left);
+      sched[chunks++] = take;
+      left -= take;
+    }
+    if (const char* e = getenv("FA_B200_HOST_CHUNKS")) {   // A/B aid: N equal chunks
+      const int64_t n = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(bh, kHostMaxChunks), atoi(e)));
+      const int64_t per = (bh + n - 1) / n;
+      chunks = 0;
+      for (int64_t h0 = 0; h0 < bh; h0 += per) sched[chunks++] = std::min<int64_t>(per, bh - h0);
+    }
+    if (const char* e = getenv("FA_B200_HOST_SCHED")) {    // A/B aid: explicit heads per chunk, e.g. "6,5,3,1,1" (rest -> last)
+      chunks = 0;
+      int64_t left2 = bh;
+      const char* c = e;
+      while (*c && left2 > 0 && chunks < kHostMaxChunks - 1) {
+        const int64_t v = std::max<int64_t>(1, std::min<int64_t>(left2, atoll(c)));
+        sched[chunks++] = v;
+        left2 -= v;
+        while (*c && *c != ',') ++c;
+        if (*c == ',') ++c;
+      }
+      if (left2 > 0) sched[chunks++] = left2;
+    }
+  }
+  int64_t h0 = 0;
+  for (int g = 0; g < chunks; ++g) {
+    const int64_t nh = sched[g];
     char* dq = (char*)s.q + h0 * row_q; char* dk = (char*)s.k + h0 * row_kv; char* dv = (char*)s.v + h0 * row_kv;
     char* dout = (char*)s.o + h0 * row_q;
     FA_CUDA(cudaMemcpyAsync(dq, (const char*)qh + h0 * row_q, nh * row_q, cudaMemcpyHostToDevice, s.st_in));
@@ -504,6 +537,7 @@ int fa_forward_host(const void* qh, const void* kh, const void* vh, void* oh, in
     FA_CUDA(cudaEventRecord(s.ev_run[g], s.st_run));
     FA_CUDA(cudaStreamWaitEvent(s.st_out, s.ev_run[g], 0));
     FA_CUDA(cudaMemcpyAsync((char*)oh + h0 * row_q, dout, nh * row_q, cudaMemcpyDeviceToHost, s.st_out));
+    h0 += nh;
   }
   FA_CUDA(cudaStreamSynchronize(s.st_out));
   return FA_OK;

@@ -52,7 +52,10 @@
                           // instances the per-element P truncation breaks register pairing and costs ~150 extra moves)
 #endif
 #ifndef FA_OPT_POLY
-#define FA_OPT_POLY 0     // of every 8 P elements, how many get exp2 from the FMA-pipe polynomial instead of MUFU.EX2 (0, 2, 4)
+#define FA_OPT_POLY -1    // of every 8 P elements, how many get exp2 from the FMA-pipe polynomial instead of MUFU.EX2 (0, 2, 4);
+                          // -1 = per instance (FwdTraits::kPoly): 2 where it measured faster (bf16, where the polynomial runs on
+                          // packed FFMA2/FADD2; tf32 d=32), 0 for tf32 d=64 (scalar polynomial: the issue slots cost more than
+                          // the MUFU time saved) — profiles/r01_ab_poly_persistent.log
 #endif
 // -DFA_TRACE=1 builds a timeline-tracing kernel: CTA 0 records clock64() at every pipeline hand-off of its first
 // kTraceSteps KV tiles into FwdParams::trace ([role 0..3][step][slot 0..7]); see scripts/trace_report.py.
@@ -112,6 +115,7 @@ struct FwdTraits {
   static constexpr int kNBuf = kDChunks == 1 ? 8 : 5;          // K/V ring depth (tiles)
   static constexpr int kUmmaK = 32 / kInSize;                  // K per tcgen05.mma: 8 (tf32) / 16 (bf16)
   static constexpr int kQSets = kDChunks == 1 ? 2 : 1;         // Q double-buffered across items where SMEM allows
+  static constexpr int kPoly = FA_OPT_POLY >= 0 ? FA_OPT_POLY : (kTF32 ? (kHeadDim == 32 ? 2 : 0) : 2);
   static constexpr int kSmemData = (2 * kQSets + kNBuf) * kTileBytes;
   static constexpr int kNumBarriers = 4 * kQSets /*q full, q free*/ + 2 * kNBuf + 2 /*s_full*/ + 4 /*p_full halves*/ +
                                       2 /*o_final*/ + 2 /*o_free*/ + 2 * kWorkQueue;
@@ -560,8 +564,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
       for (int i = i0; i < i0 + 32; i += 4) {
         // which of these 4 elements take the polynomial route: the first FA_OPT_POLY/2 pairs of every 8 elements
-        const bool kPoly01 = (FA_OPT_POLY >= 2) && ((i & 4) == 0);
-        const bool kPoly23 = (FA_OPT_POLY >= 4) && ((i & 4) == 0);
+        const bool kPoly01 = (T::kPoly >= 2) && ((i & 4) == 0);
+        const bool kPoly23 = (T::kPoly >= 4) && ((i & 4) == 0);
         bool packed = false;
 #if FA_OPT_F2
         if constexpr (!kTF32) {

@@ -39,8 +39,22 @@ FA_DEVINL void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
                : "memory");
 }
+// FA_WAIT_HINT_NS > 0: pass a suspend-time hint, so a waiting warp sleeps in hardware instead of re-issuing the
+// try_wait (A/B aid: does a spinning warp take issue slots from the softmax warp on the same sub-partition?)
+#ifndef FA_WAIT_HINT_NS
+#define FA_WAIT_HINT_NS 0
+#endif
 FA_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if FA_WAIT_HINT_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(static_cast<uint32_t>(FA_WAIT_HINT_NS))
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -48,6 +62,7 @@ FA_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 FA_DEVINL void mbar_wait(uint32_t bar, uint32_t parity, uint32_t tag) {
