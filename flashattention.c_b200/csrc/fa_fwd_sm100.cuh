@@ -51,11 +51,31 @@
 #define FA_OPT_F2 1       // packed FFMA2 / FADD2 for the scale-subtract and the row sum (bf16 instances only: in the tf32
                           // instances the per-element P truncation breaks register pairing and costs ~150 extra moves)
 #endif
-#ifndef FA_OPT_POLY
-#define FA_OPT_POLY -1    // of every 8 P elements, how many get exp2 from the FMA-pipe polynomial instead of MUFU.EX2 (0, 2, 4);
-                          // -1 = per instance (FwdTraits::kPoly): 2 where it measured faster (bf16, where the polynomial runs on
-                          // packed FFMA2/FADD2; tf32 d=32), 0 for tf32 d=64 (scalar polynomial: the issue slots cost more than
-                          // the MUFU time saved) — profiles/r01_ab_poly_persistent.log
+#ifndef FA_OPT_TF32_COMP
+#define FA_OPT_TF32_COMP 1  // tf32 instances: instead of truncating every P element to tf32 before it is summed (one LOP3 per
+                            // element, which also keeps the packed FFMA2/FADD2 forms from being used), P is computed as
+                            // P*(1+eps) — eps = the mean relative truncation error of a tf32 operand, folded into the exp2
+                            // argument for free — so that what the tensor core reads (P*(1+eps) truncated) is P on average, and
+                            // the row sum of the untruncated values is divided by (1+eps) once per row in the epilogue
+#endif
+#ifndef FA_OPT_SPLIT_KEYS
+#define FA_OPT_SPLIT_KEYS 64  // (96 measured 2-3% slower: profiles/r01_ab_tf32_comp.log) P is handed to the MMA warp in two pieces: keys [0, FA_OPT_SPLIT_KEYS) and the rest (64 or 96)
+#endif
+// Of every FA_POLY_DEN_x consecutive element pairs of a P row, the first FA_POLY_NUM_x get exp2 from the FMA-pipe
+// polynomial (packed FFMA2/FADD2) instead of MUFU.EX2: the softmax is MUFU-bound (16 ex2/clk/SM), the polynomial moves part
+// of that load to the FMA pipe.  Measured on B200 (profiles/r01_ab_poly_persistent.log, r01_ab_tf32_comp.log):
+// 1/4 is +7% (bf16 d128) / +9% (tf32 d64), 1/2 is slower than none.
+#ifndef FA_POLY_NUM_BF16
+#define FA_POLY_NUM_BF16 1
+#endif
+#ifndef FA_POLY_DEN_BF16
+#define FA_POLY_DEN_BF16 4
+#endif
+#ifndef FA_POLY_NUM_TF32
+#define FA_POLY_NUM_TF32 1
+#endif
+#ifndef FA_POLY_DEN_TF32
+#define FA_POLY_DEN_TF32 4
 #endif
 // -DFA_TRACE=1 builds a timeline-tracing kernel: CTA 0 records clock64() at every pipeline hand-off of its first
 // kTraceSteps KV tiles into FwdParams::trace ([role 0..3][step][slot 0..7]); see scripts/trace_report.py.
@@ -102,6 +122,11 @@ constexpr int kNumThreads = 320;      // 8 softmax warps + TMA producer warp + M
 constexpr int kBarMerge = 3;          // named barrier: slot B hands its partial (m, l) to slot A (split-KV tail items)
 constexpr int kWorkQueue = 4;         // depth of the SMEM item queue (the producer is at most two items ahead)
 constexpr float kRescaleThreshold = 8.0f;  // lazy rescale: keep a stale max while it is within 2^8
+// tf32 truncation compensation (FA_OPT_TF32_COMP): an operand with a log-uniform mantissa loses on average
+// eps = 2^-11 / (2 ln 2) of its value when the tensor core drops the low 13 mantissa bits
+constexpr float kTf32CompEps = 3.5222e-4f;
+constexpr float kTf32CompLog2 = 5.0806e-4f;          // log2(1 + eps), added to the exp2 argument
+constexpr float kTf32CompInv = 1.0f / (1.0f + kTf32CompEps);
 
 template <bool kTF32, int kHeadDim, bool kOutF32>
 struct FwdTraits {
@@ -115,7 +140,12 @@ struct FwdTraits {
   static constexpr int kNBuf = kDChunks == 1 ? 8 : 5;          // K/V ring depth (tiles)
   static constexpr int kUmmaK = 32 / kInSize;                  // K per tcgen05.mma: 8 (tf32) / 16 (bf16)
   static constexpr int kQSets = kDChunks == 1 ? 2 : 1;         // Q double-buffered across items where SMEM allows
-  static constexpr int kPoly = FA_OPT_POLY >= 0 ? FA_OPT_POLY : (kTF32 ? (kHeadDim == 32 ? 2 : 0) : 2);
+  static constexpr bool kComp = kTF32 && (FA_OPT_TF32_COMP != 0);   // tf32 truncation compensated instead of reproduced
+  static constexpr bool kPacked = (FA_OPT_F2 != 0) && (!kTF32 || kComp);   // FFMA2 / FADD2 forms in the exp loop
+  static constexpr int kSplitKeys = FA_OPT_SPLIT_KEYS;
+  static_assert(kSplitKeys == 64 || kSplitKeys == 96, "P split point");
+  static constexpr int kPolyNum = kTF32 ? FA_POLY_NUM_TF32 : FA_POLY_NUM_BF16;   // polynomial exp2 on kPolyNum of every
+  static constexpr int kPolyDen = kTF32 ? FA_POLY_DEN_TF32 : FA_POLY_DEN_BF16;   // kPolyDen element pairs (packed path only)
   static constexpr int kSmemData = (2 * kQSets + kNBuf) * kTileBytes;
   static constexpr int kNumBarriers = 4 * kQSets /*q full, q free*/ + 2 * kNBuf + 2 /*s_full*/ + 4 /*p_full halves*/ +
                                       2 /*o_final*/ + 2 /*o_free*/ + 2 * kWorkQueue;
@@ -374,6 +404,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint64_t hi_mnmajor = p.v_desc_hi;
     constexpr int kKStepsS = kHeadDim / T::kUmmaK;   // k-steps of Q K^T (32 bytes each)
     constexpr int kKStepsPV = kBlockN / T::kUmmaK;   // k-steps of P V (UmmaK keys each)
+    constexpr int kKStepsSplit = T::kSplitKeys / T::kUmmaK;   // k-steps covered by the first piece of P
     // Descriptors are built once per operand tile; a k-step only adds to the 14-bit start-address field
     // ((bytes >> 4); SMEM addresses are < 2^18, so the field never carries).
     auto issue_s = [&](int t, int qbuf, int buf) {
@@ -433,7 +464,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_wait(bar_p + 16 * t, par, TAG_P_FULL);            // keys [0, 64) of P are in TMEM
       tc_fence_after();
       FA_TRACE_AT(2 + t, g, 1);
-      if (elect_one_sync()) issue_pv(t, vbuf, j > 0, 0, kKStepsPV / 2);
+      if (elect_one_sync()) issue_pv(t, vbuf, j > 0, 0, kKStepsSplit);
       __syncwarp();
       FA_TRACE_AT(2 + t, g, 2);
 #endif
@@ -441,7 +472,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tc_fence_after();
       FA_TRACE_AT(2 + t, g, 3);
       if (elect_one_sync()) {
-        issue_pv(t, vbuf, j > 0, FA_OPT_SPLITP ? kKStepsPV / 2 : 0, kKStepsPV);
+        issue_pv(t, vbuf, j > 0, FA_OPT_SPLITP ? kKStepsSplit : 0, kKStepsPV);
         if (release) tc_commit(bar_empty + 8 * vbuf);
         if (last) {
           tc_commit(bar_o + 8 * t);
@@ -563,12 +594,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     auto exp_chunk = [&](float* s, const int i0, const float neg_mc, float& l0, float& l1, float& l2, float& l3) {
 #pragma unroll
       for (int i = i0; i < i0 + 32; i += 4) {
-        // which of these 4 elements take the polynomial route: the first FA_OPT_POLY/2 pairs of every 8 elements
-        const bool kPoly01 = (T::kPoly >= 2) && ((i & 4) == 0);
-        const bool kPoly23 = (T::kPoly >= 4) && ((i & 4) == 0);
+        // which of these two element pairs take the polynomial route
+        const bool kPoly01 = T::kPacked && ((i >> 1) % T::kPolyDen) < T::kPolyNum;
+        const bool kPoly23 = T::kPacked && (((i >> 1) + 1) % T::kPolyDen) < T::kPolyNum;
         bool packed = false;
 #if FA_OPT_F2
-        if constexpr (!kTF32) {
+        if constexpr (T::kPacked) {
           packed = true;
           float2 a01 = ffma2(make_float2(s[i], s[i + 1]), make_float2(c, c), make_float2(neg_mc, neg_mc));
           float2 a23 = ffma2(make_float2(s[i + 2], s[i + 3]), make_float2(c, c), make_float2(neg_mc, neg_mc));
@@ -608,7 +639,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             s[i + 2] = ex2(fmaf(s[i + 2], c, neg_mc));
             s[i + 3] = ex2(fmaf(s[i + 3], c, neg_mc));
           }
-          if constexpr (kTF32) {
+          if constexpr (kTF32 && !T::kComp) {
             // kind::tf32 reads only the top 19 bits of P; sum exactly those values so that O = (sum P~ V) / (sum P~)
             // is normalised by what the tensor core actually multiplied (removes the truncation bias from O)
             s[i] = __uint_as_float(__float_as_uint(s[i]) & 0xFFFFE000u);
@@ -688,22 +719,25 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
         }
         const float m_safe = (m == -INFINITY) ? 0.f : m;
-        const float neg_mc = -m_safe * c;
-        // P = exp2(s*c - m*c) in two 64-key halves; each half is written to TMEM and handed to the MMA warp as soon
-        // as it is complete, so the first half of P*V runs under the second half of the exps.
+        const float neg_mc = T::kComp ? fmaf(-m_safe, c, kTf32CompLog2) : -m_safe * c;
+        // P = exp2(s*c - m*c) in two pieces (keys [0, kSplitKeys) and the rest); each piece is written to TMEM and handed
+        // to the MMA warp as soon as it is complete, so most of P*V runs under the exps of the last piece and only a
+        // short P*V remains between the last arrival and the next Q*K^T.
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        constexpr int kChunks0 = T::kSplitKeys / 32;   // 32-key chunks in the first piece
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          exp_chunk(s, h * 64, neg_mc, l0, l1, l2, l3);
-          exp_chunk(s, h * 64 + 32, neg_mc, l0, l1, l2, l3);
-          if constexpr (kTF32) {
-            tmem_st32(tS + h * 64, reinterpret_cast<uint32_t*>(&s[h * 64]));
-            tmem_st32(tS + h * 64 + 32, reinterpret_cast<uint32_t*>(&s[h * 64 + 32]));
-          } else {
-            uint32_t pk[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(s[h * 64 + 2 * i], s[h * 64 + 2 * i + 1]);
-            tmem_st32(tS + h * 32, &pk[0]);
+          for (int cc = (h == 0 ? 0 : kChunks0); cc < (h == 0 ? kChunks0 : 4); ++cc) {
+            exp_chunk(s, cc * 32, neg_mc, l0, l1, l2, l3);
+            if constexpr (kTF32) {
+              tmem_st32(tS + cc * 32, reinterpret_cast<uint32_t*>(&s[cc * 32]));
+            } else {
+              uint32_t pk[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(s[cc * 32 + 2 * i], s[cc * 32 + 2 * i + 1]);
+              tmem_st16(tS + cc * 16, pk);
+            }
           }
 #if FA_OPT_SPLITP
           if (tracer) FA_TRACE_AT(t, g, 3 + 2 * h);
@@ -723,6 +757,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         l += (l0 + l1) + (l2 + l3);
       }
+      if constexpr (T::kComp) l *= kTf32CompInv;   // the sums were taken over P*(1+eps)
 
       // ---- epilogue: O/l -> swizzled SMEM (reusing this slot's Q buffer) -> TMA store; LSE -> global ----
       if (tracer && seq == 0) FA_TRACE_MISC(t, 2);
