@@ -239,7 +239,7 @@ def run_ours(args, torch, dist, rank, world, device):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/); None = not captured
-TRAFFIC_BYTES = {"C2": 117.9e6, "C4": 1058.6e6}   # profiles/r01_ncu_summary.md (v5 kernel)
+TRAFFIC_BYTES = {"C2": 115.6e6, "C4": 1058.4e6}   # dram__bytes_read+write per launch, profiles/r01_ncu_summary.md (v8 kernel)
 
 
 def other_configs(torch, fab, device, flush, peaks):

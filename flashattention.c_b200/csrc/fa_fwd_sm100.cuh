@@ -58,6 +58,13 @@
                             // argument for free — so that what the tensor core reads (P*(1+eps) truncated) is P on average, and
                             // the row sum of the untruncated values is divided by (1+eps) once per row in the epilogue
 #endif
+#ifndef FA_OPT_EARLY_S
+#define FA_OPT_EARLY_S 0  // instances with spare TMEM columns (head dim <= 64): the second piece of P is written to its own
+                          // columns instead of over S, so the next Q*K^T no longer has to wait for it — it is issued right
+                          // after the first piece's P*V, while the softmax warps are still in the exps of the second piece.
+                          // Correct (62 GPU tests) but measured 3-7% slower (profiles/r01_ab_early_s.log): with one in-order
+                          // issuer the other slot's work queues behind this slot's second-piece wait
+#endif
 #ifndef FA_OPT_SPLIT_KEYS
 #define FA_OPT_SPLIT_KEYS 64  // (96 measured 2-3% slower: profiles/r01_ab_tf32_comp.log) P is handed to the MMA warp in two pieces: keys [0, FA_OPT_SPLIT_KEYS) and the rest (64 or 96)
 #endif
@@ -148,11 +155,14 @@ struct FwdTraits {
   static constexpr int kPolyDen = kTF32 ? FA_POLY_DEN_TF32 : FA_POLY_DEN_BF16;   // kPolyDen element pairs (packed path only)
   static constexpr int kSmemData = (2 * kQSets + kNBuf) * kTileBytes;
   static constexpr int kNumBarriers = 4 * kQSets /*q full, q free*/ + 2 * kNBuf + 2 /*s_full*/ + 4 /*p_full halves*/ +
-                                      2 /*o_final*/ + 2 /*o_free*/ + 2 * kWorkQueue;
+                                      2 /*o_final*/ + 2 /*o_free*/ + 2 * kWorkQueue + 2 /*pv1 done*/;
   static constexpr int kSmemBytes = kSmemData + kNumBarriers * 8 + 16 /*tmem ptr*/ + kWorkQueue * 4 + 2 * kBlockM * 4 /*m, l*/ +
                                     1024 /*alignment slack*/;
   static constexpr int kTmemS = 0;        // + 128*t
   static constexpr int kTmemO = 256;      // + kHeadDim*t
+  static constexpr int kP1Cols = (kBlockN - kSplitKeys) * kInSize / 4;   // TMEM columns of the second piece of P
+  static constexpr int kTmemP1 = 256 + 2 * kHeadDim;                      // + kP1Cols*t (kEarlyS only)
+  static constexpr bool kEarlyS = (FA_OPT_EARLY_S != 0) && (FA_OPT_SPLITP != 0) && (256 + 2 * kHeadDim + 2 * kP1Cols <= 512);
   static_assert(kDChunks == 1 || kDChunks == 2, "tile row must be 128 or 256 bytes");
   static_assert(256 + 2 * kHeadDim <= 512, "TMEM budget");
 };
@@ -160,7 +170,7 @@ struct FwdTraits {
 // watchdog tags
 enum : uint32_t {
   TAG_Q_FULL = 1, TAG_KV_FULL = 2, TAG_KV_EMPTY = 3, TAG_S_FULL = 4, TAG_P_FULL = 5, TAG_O_FINAL = 6, TAG_Q_FREE = 7,
-  TAG_O_FREE = 8, TAG_W_FULL = 9, TAG_W_EMPTY = 10
+  TAG_O_FREE = 8, TAG_W_FULL = 9, TAG_W_EMPTY = 10, TAG_PV1 = 11
 };
 
 // What one work item is, derived from its index by every warp role on its own.
@@ -236,7 +246,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const uint32_t bar_ofree = bar_o + 16;                      // [2]  slot t's epilogue has read its accumulator(s) out of TMEM
   const uint32_t bar_wfull = bar_ofree + 16;                  // [kWorkQueue]
   const uint32_t bar_wempty = bar_wfull + 8 * kWorkQueue;     // [kWorkQueue]
-  const uint32_t s_tmem_ptr = bar_wempty + 8 * kWorkQueue;    // 16 bytes
+  const uint32_t bar_pv1 = bar_wempty + 8 * kWorkQueue;       // [2]  second-piece P*V of slot t's latest step has completed
+  const uint32_t s_tmem_ptr = bar_pv1 + 16;                   // 16 bytes
   const uint32_t s_work = s_tmem_ptr + 16;                    // [kWorkQueue] item indices (-1 = no more work)
   const uint32_t s_ml = s_work + 4 * kWorkQueue;              // m[128], l[128] of slot B (split-KV merge)
 
@@ -261,6 +272,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_init(bar_p + 16 * t, 128);
       mbar_init(bar_p + 16 * t + 8, 128);
       mbar_init(bar_o + 8 * t, 1);
+      mbar_init(bar_pv1 + 8 * t, 1);
     }
     mbar_init(bar_ofree, 4);              // one arrival per softmax warp of the slot, only in items where it read TMEM
     mbar_init(bar_ofree + 8, 4);
@@ -327,6 +339,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           const int round = ring / T::kNBuf;
           ++ring;
           if (round > 0) mbar_wait(bar_empty + 8 * buf, (round - 1) & 1, TAG_KV_EMPTY);
+#if FA_TRACE
+          if (seq == 0) FA_TRACE_AT(tm == &tm_k ? 2 : 3, kv_tile, 4);   // ring slot free -> TMA issued (first item: tile == step)
+#endif
           mbar_arrive_expect_tx(bar_full + 8 * buf, T::kTileBytes);
 #pragma unroll
           for (int c = 0; c < T::kDChunks; ++c)
@@ -421,7 +436,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     auto issue_pv = [&](int t, int buf, bool accumulate, int ks0, int ks1) {
       const uint64_t vd = sdesc_at(hi_mnmajor, sKV + buf * T::kTileBytes);
       const uint32_t d = tmem_base + T::kTmemO + t * kHeadDim;
-      const uint32_t a = tmem_base + T::kTmemS + t * kBlockN;
+      // P aliases S; with kEarlyS the second piece (k-steps >= kKStepsSplit) has its own columns
+      const bool own = T::kEarlyS && ks0 >= kKStepsSplit;
+      const uint32_t a = own ? tmem_base + T::kTmemP1 + t * T::kP1Cols - kKStepsSplit * 8 : tmem_base + T::kTmemS + t * kBlockN;
 #pragma unroll
       for (int ks = ks0; ks < ks1; ++ks) {
         mma_ts<kTF32>(d, a + ks * 8, vd + static_cast<uint32_t>(ks * (T::kUmmaK * 128 / 16)), idesc_pv,
@@ -459,6 +476,31 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #if FA_TRACE
       const int g = t == 0 ? steps_a++ : steps_b++;
 #endif
+      if constexpr (T::kEarlyS) {
+        FA_TRACE_AT(2 + t, g, 0);
+        mbar_wait(bar_p + 16 * t, par, TAG_P_FULL);            // first piece of P is in TMEM (over S), all of S_t(j) is in registers
+        tc_fence_after();
+        FA_TRACE_AT(2 + t, g, 1);
+        if (elect_one_sync()) {
+          issue_pv(t, vbuf, j > 0, 0, kKStepsSplit);
+          if (!last) {
+            issue_s(t, qbuf, kbuf);                            // in order after the P*V that read the aliased columns
+            tc_commit(bar_s + 8 * t);
+            if (release) tc_commit(bar_empty + 8 * kbuf);
+          }
+        }
+        __syncwarp();
+        FA_TRACE_AT(2 + t, g, 2);
+        mbar_wait(bar_p + 16 * t + 8, par, TAG_P_FULL);        // second piece (own columns)
+        tc_fence_after();
+        FA_TRACE_AT(2 + t, g, 3);
+        if (elect_one_sync()) {
+          issue_pv(t, vbuf, true, kKStepsSplit, kKStepsPV);
+          tc_commit(bar_pv1 + 8 * t);                          // the piece's columns are free again; O_t holds all of step j
+          if (release) tc_commit(bar_empty + 8 * vbuf);
+          if (last) tc_commit(bar_o + 8 * t);
+        }
+      } else {
 #if FA_OPT_SPLITP
       FA_TRACE_AT(2 + t, g, 0);
       mbar_wait(bar_p + 16 * t, par, TAG_P_FULL);            // keys [0, 64) of P are in TMEM
@@ -481,6 +523,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           tc_commit(bar_s + 8 * t);
           if (release) tc_commit(bar_empty + 8 * kbuf);
         }
+      }
       }
       __syncwarp();
       FA_TRACE_AT(2 + t, g, 6);
@@ -528,6 +571,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           wait_full(iv);
           if (j + 1 < w.n_max) wait_full(ik);
           tc_fence_after();
+#if FA_TRACE
+          FA_TRACE_AT(2, steps_a, 7);      // K/V of this step landed (slot 0 of the same row = step start)
+#endif
 #pragma unroll
           for (int t = 0; t < 2; ++t)
             if (j < w.n(t)) step(t, j, j == w.n(t) - 1, set * 2 + t, vbuf, kbuf, false);
@@ -536,6 +582,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             if (j + 1 < w.n_max) tc_commit(bar_empty + 8 * kbuf);
           }
           __syncwarp();
+#if FA_TRACE
+          FA_TRACE_AT(3, steps_b - 1, 7);  // ring slots of this step released
+#endif
         }
       } else {
         // ---- split-KV: each slot has its own K/V tiles; ring order K_A0, K_B0, then V_A(j), K_A(j+1), V_B(j), K_B(j+1) ----
@@ -584,6 +633,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint32_t tS = tmem_base + lane_base + T::kTmemS + t * kBlockN;
     const uint32_t tO = tmem_base + lane_base + T::kTmemO + t * kHeadDim;
     const uint32_t tO_other = tmem_base + lane_base + T::kTmemO + (t ^ 1) * kHeadDim;
+    const uint32_t tP1 = tmem_base + lane_base + T::kTmemP1 + t * T::kP1Cols;   // second piece of P (kEarlyS)
     const float c = p.scale_log2;
     const bool tracer = (warp & 3) == 0 && lane == 0;
     (void)tracer;
@@ -703,6 +753,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           // lazy rescale: only move the reference max when it grew by more than 2^kRescaleThreshold
           const bool need = (m_new - m) * c > kRescaleThreshold;   // (-inf -> finite) gives +inf -> true
           if (__any_sync(0xffffffffu, need)) {
+            if constexpr (T::kEarlyS) {
+              // S_t(j) no longer implies that all of P_t(j-1) V has retired: wait for its second piece before touching O_t
+              mbar_wait(bar_pv1 + 8 * t, (g - 1) & 1, TAG_PV1);
+              tc_fence_after();
+            }
             const float m_use = need ? m_new : m;
             const float alpha = need ? ex2((m - m_use) * c) : 1.0f;  // m = -inf -> 0
             l *= alpha;
@@ -730,13 +785,20 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
           for (int cc = (h == 0 ? 0 : kChunks0); cc < (h == 0 ? kChunks0 : 4); ++cc) {
             exp_chunk(s, cc * 32, neg_mc, l0, l1, l2, l3);
+            const bool own = T::kEarlyS && h == 1;   // second piece in its own columns
+            if (own && cc == kChunks0 && g > 0) {
+              // the previous step's second-piece P*V must have read these columns (long done: it was issued a whole
+              // softmax step ago)
+              mbar_wait(bar_pv1 + 8 * t, (g - 1) & 1, TAG_PV1);
+              tc_fence_after();
+            }
             if constexpr (kTF32) {
-              tmem_st32(tS + cc * 32, reinterpret_cast<uint32_t*>(&s[cc * 32]));
+              tmem_st32(own ? tP1 + (cc - kChunks0) * 32 : tS + cc * 32, reinterpret_cast<uint32_t*>(&s[cc * 32]));
             } else {
               uint32_t pk[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(s[cc * 32 + 2 * i], s[cc * 32 + 2 * i + 1]);
-              tmem_st16(tS + cc * 16, pk);
+              tmem_st16(own ? tP1 + (cc - kChunks0) * 16 : tS + cc * 16, pk);
             }
           }
 #if FA_OPT_SPLITP

@@ -34,6 +34,18 @@ def main(path, lo=8, hi=40):
         if (mm[lo:hi, 6] >= 0).all():
             print(f"tile {'AB'[t]}: S(j+1) issued+committed -> softmax wakes {np.mean(sm[lo + 1:hi + 1, 1] - mm[lo:hi, 6]):8.0f}   (= MMA execution + commit + wake-up)")
             print(f"tile {'AB'[t]}: last P arrive -> softmax wakes on S(j+1) {np.mean(sm[lo + 1:hi + 1, 1] - sm[lo:hi, 6]):8.0f}")
+    # MMA warp between two K/V steps: end of B's step (role 3 slot 6) -> ring slots released (role 3 slot 7) -> next step's
+    # K/V landed (role 2 slot 7) -> step start (role 2 slot 0)
+    if (r[3, lo:hi, 7] >= 0).all() and (r[2, lo + 1:hi + 1, 7] >= 0).all():
+        print(f"MMA warp: B step end -> slots released {np.mean(r[3, lo:hi, 7] - r[3, lo:hi, 6]):6.0f} | released -> next K/V landed "
+              f"{np.mean(r[2, lo + 1:hi + 1, 7] - r[3, lo:hi, 7]):6.0f} | landed -> A step start {np.mean(r[2, lo + 1:hi + 1, 0] - r[2, lo + 1:hi + 1, 7]):6.0f}")
+        print(f"MMA warp: A step end -> B step start {np.mean(r[3, lo:hi, 0] - r[2, lo:hi, 6]):6.0f} | A step {np.mean(r[2, lo:hi, 6] - r[2, lo:hi, 0]):6.0f} | B step {np.mean(r[3, lo:hi, 6] - r[3, lo:hi, 0]):6.0f}")
+    # producer: TMA issue time of K_j (role 2 slot 4, row j) / V_j (role 3 slot 4, row j) vs the MMA warp seeing V_j and K_{j+1}
+    # landed (role 2 slot 7, row j)
+    if (r[2, lo:hi + 1, 4] >= 0).all() and (r[2, lo:hi, 7] >= 0).all():
+        print(f"producer: K_(j+1) TMA issued -> MMA warp has V_j and K_(j+1) {np.mean(r[2, lo:hi, 7] - r[2, lo + 1:hi + 1, 4]):6.0f} | "
+              f"V_j issued -> same {np.mean(r[2, lo:hi, 7] - r[3, lo:hi, 4]):6.0f} | slots of step j released -> K_(j+3) issued "
+              f"{np.mean(r[2, lo + 3:hi + 3, 4] - r[3, lo:hi, 7]):6.0f}")
     print("raw, first rows (role, step, slots):")
     for role in range(4):
         for j in range(lo, lo + 3):
