@@ -10,7 +10,7 @@ Host-side mirror of the reference interface (names, argument meaning, error beha
 Everything runs on hand-written sm_100a kernels through the C-ABI library libfa_b200.so
 (include/fa_b200.h).  There is no CPU or eager-PyTorch fallback: without the library or a B200 the calls raise.
 """
-from ._lib import FA_BF16, FA_F32, FA_IMPL_AUTO, FA_IMPL_SIMT, FA_IMPL_TCGEN05, FaError, lib  # noqa: F401
+from ._lib import FA_BF16, FA_F32, FA_FLAG_BATCH_INVARIANT, FA_IMPL_AUTO, FA_IMPL_SIMT, FA_IMPL_TCGEN05, FaError, lib  # noqa: F401
 from .api import (  # noqa: F401
     attention,
     attention_forward,
@@ -22,6 +22,6 @@ from .api import (  # noqa: F401
     load_extension,
     merge_partials,
 )
-from .ring import bh_shard_range, ring_attention, sharded_attention  # noqa: F401
+from .ring import bh_shard_range, ring_attention, sharded_attention, zigzag_shard, zigzag_step_plan, zigzag_unshard  # noqa: F401
 
 __version__ = "0.1.0"

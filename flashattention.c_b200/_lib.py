@@ -10,6 +10,7 @@ LIB_PATH = PKG_DIR / "libfa_b200.so"
 
 FA_F32, FA_BF16 = 0, 1
 FA_IMPL_AUTO, FA_IMPL_TCGEN05, FA_IMPL_SIMT = 0, 1, 2
+FA_FLAG_BATCH_INVARIANT = 1
 
 # every symbol include/fa_b200.h declares (tests check that the built library exports all of them)
 EXPORTED_SYMBOLS = [
@@ -30,7 +31,7 @@ class FaParams(ctypes.Structure):
         ("k_stride_b", ctypes.c_int64), ("k_stride_h", ctypes.c_int64), ("k_stride_n", ctypes.c_int64),
         ("v_stride_b", ctypes.c_int64), ("v_stride_h", ctypes.c_int64), ("v_stride_n", ctypes.c_int64),
         ("o_stride_b", ctypes.c_int64), ("o_stride_h", ctypes.c_int64), ("o_stride_n", ctypes.c_int64),
-        ("impl", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("impl", ctypes.c_int32), ("flags", ctypes.c_int32),
     ]
 
 

@@ -46,14 +46,34 @@ def _shape4(Q, K, V):
     return b, h, nq, nk, d
 
 
-def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False, impl=_lib.FA_IMPL_AUTO, out=None):
+def _tma_view(t: torch.Tensor) -> torch.Tensor:
+    """A strided view is passed to the kernel as it is (the strides go into the TMA tensor map: sequence slices, packed or
+    head-interleaved layouts need no copy) when its last axis is contiguous and base and strides are 16-byte aligned;
+    anything else is made contiguous first."""
+    es = t.element_size()
+    ok = t.stride(-1) == 1 and t.data_ptr() % 16 == 0 and all((s * es) % 16 == 0 for s in t.stride()[:-1])
+    return t if ok else t.contiguous()
+
+
+def _strides_bhn(t: torch.Tensor):
+    """(batch, head, row) strides in elements of a [B*H, N, d] or [B, H, N, d] tensor."""
+    if t.dim() == 3:
+        return t.stride(0) * t.shape[0], t.stride(0), t.stride(1)
+    return t.stride(0), t.stride(1), t.stride(2)
+
+
+def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False, impl=_lib.FA_IMPL_AUTO, out=None,
+              batch_invariant=False):
     """O = softmax(scale * Q K^T [+ causal mask]) V.   scale defaults to 1/sqrt(d).
 
-    Q, K, V: contiguous CUDA tensors [B*H, N, d] or [B, H, N, d], float32 or bfloat16.
+    Q, K, V: CUDA tensors [B*H, N, d] or [B, H, N, d], float32 or bfloat16; strided views with a contiguous last axis
+    (e.g. a slice of the sequence axis) are read in place.
     Returns O (same shape/dtype as Q; float32 if out_f32) and, if return_lse, LSE float32 [..., N].
+    batch_invariant: FA_FLAG_BATCH_INVARIANT — a (batch, head) slice gives bit-identical results whatever else is in the
+    launch (alone, in a larger batch, on another rank of a B x H sharded job); costs the split-KV tail optimisation.
     """
     b, h, nq, nk, d = _shape4(Q, K, V)
-    Q, K, V = Q.contiguous(), K.contiguous(), V.contiguous()
+    Q, K, V = _tma_view(Q), _tma_view(K), _tma_view(V)
     if scale is None:
         scale = 1.0 / math.sqrt(d)
     with torch.cuda.device(Q.device):
@@ -70,12 +90,12 @@ def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False
         p.causal = 1 if causal else 0
         p.o_f32 = 1 if (out_f32 and Q.dtype == torch.bfloat16) else 0
         p.scale = float(scale)
-        p.q_stride_n = p.k_stride_n = p.v_stride_n = p.o_stride_n = d
-        p.q_stride_h, p.o_stride_h = nq * d, nq * d
-        p.k_stride_h = p.v_stride_h = nk * d
-        p.q_stride_b, p.o_stride_b = h * nq * d, h * nq * d
-        p.k_stride_b = p.v_stride_b = h * nk * d
+        (p.q_stride_b, p.q_stride_h, p.q_stride_n) = _strides_bhn(Q)
+        (p.k_stride_b, p.k_stride_h, p.k_stride_n) = _strides_bhn(K)
+        (p.v_stride_b, p.v_stride_h, p.v_stride_n) = _strides_bhn(V)
+        p.o_stride_n, p.o_stride_h, p.o_stride_b = d, nq * d, h * nq * d
         p.impl = int(impl)
+        p.flags = _lib.FA_FLAG_BATCH_INVARIANT if batch_invariant else 0
         check(lib().fa_forward_ex(ctypes.byref(p), ctypes.c_void_p(_stream_ptr(Q.device))), "fa_forward_ex")
     return (O, lse) if return_lse else O
 

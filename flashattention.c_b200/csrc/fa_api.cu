@@ -262,7 +262,7 @@ int run_tc(const fa_params* p, cudaStream_t st) {
     fp.n_big = (int)n_big;
     // the remainder CTAs split their K/V range over the two tile slots (FA_B200_TAIL_SPLIT=0: one slot, A/B aid)
     const char* ts = getenv("FA_B200_TAIL_SPLIT");   // read per call so a test can compare both modes in one process
-    fp.tail_split = (ts && atoi(ts) == 0) ? 0 : 1;
+    fp.tail_split = ((ts && atoi(ts) == 0) || (p->flags & FA_FLAG_BATCH_INVARIANT)) ? 0 : 1;
     const int64_t n_items = n_big + 2 * (nb - n_big);
     if (n_items > 0x7fffffff) return FA_ERR_INVALID_ARG;
     fp.n_items = (int)n_items;

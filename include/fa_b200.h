@@ -46,6 +46,14 @@ enum fa_impl {
   FA_IMPL_SIMT = 2      /* CUDA-core general-shape kernel (odd head dims; the on-GPU checker) */
 };
 
+enum fa_flags {
+  /* Every 128-row query tile is computed by the same sequence of operations whatever else is in the launch, so a
+   * (batch, head) slice gives bit-identical results alone, inside a larger batch, or on another rank of a B x H
+   * sharded job.  Off by default: the scheduler then splits the K/V range of the last partial wave's tiles over two
+   * tile slots (split-KV with a log-sum-exp merge), which is faster for small grids but rounds differently. */
+  FA_FLAG_BATCH_INVARIANT = 1
+};
+
 /* strided problem description.  Strides are in ELEMENTS; the head_dim axis is contiguous. */
 typedef struct fa_params {
   const void* q; const void* k; const void* v;
@@ -63,7 +71,7 @@ typedef struct fa_params {
   int64_t v_stride_b, v_stride_h, v_stride_n;
   int64_t o_stride_b, o_stride_h, o_stride_n;
   int32_t impl;            /* 0 = automatic; FA_IMPL_TCGEN05 / FA_IMPL_SIMT force a kernel family (tests) */
-  int32_t reserved;
+  int32_t flags;           /* bit set of enum fa_flags (0 = defaults) */
 } fa_params;
 
 /*

@@ -42,10 +42,17 @@ def main():
     g = torch.Generator(device="cpu").manual_seed(7)
     B, H, N, d = 2, 8, 2048, 128
     q, k, v = (torch.randn(B * H, N, d, generator=g).to(torch.bfloat16).to(dev) for _ in range(3))
-    o_loc = fab.sharded_attention(q, k, v, causal=True)
+    # batch-invariant mode: the gathered shards must equal the unsharded forward bit for bit; default mode (split-KV
+    # tails, scheduled by launch size): equal within the bf16 tolerance
+    o_loc = fab.sharded_attention(q, k, v, causal=True, batch_invariant=True)
     o_all = gather_bh(o_loc, B * H)
-    o_ref = fab.attention(q, k, v, causal=True)
+    o_ref = fab.attention(q, k, v, causal=True, batch_invariant=True)
+    o_loc_d = fab.sharded_attention(q, k, v, causal=True)
+    o_all_d = gather_bh(o_loc_d, B * H)
+    o_ref_d = fab.attention(q, k, v, causal=True)
     out.append({"check": "bh_sharded_vs_single_gpu", "world": world, "bitwise_equal": bool(torch.equal(o_all, o_ref)),
+                "default_mode_max_abs_diff": float((o_all_d.float() - o_ref_d.float()).abs().max()),
+                "default_vs_batch_invariant_max_abs_diff": float((o_ref_d.float() - o_ref.float()).abs().max()),
                 "local_bh": int(o_loc.shape[0])})
 
     # ---- 2. ring parity ----
@@ -64,6 +71,20 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             out.append({"check": f"ring_vs_single_gpu dtype={str(dtype).split('.')[-1]} d={dd} causal={causal} N={Nf}", "world": world,
                         "max_err_o": float(t[0]), "max_err_lse": float(t[1]), "ok": bool(t[0] < tol and t[1] < 2e-3)})
+
+    # ---- 2b. balanced (zig-zag) causal ring parity: rank r holds chunks r and 2P-1-r ----
+    for dtype, dd, tol in ((torch.bfloat16, 128, 2e-2), (torch.float32, 64, 2e-3)):
+        Hh, Nf = 4, 1024 * world
+        gq = torch.Generator(device="cpu").manual_seed(12)
+        qf, kf, vf = (torch.randn(1, Hh, Nf, dd, generator=gq).to(dtype).to(dev) for _ in range(3))
+        o_r, lse_r = fab.ring_attention(*(fab.zigzag_shard(t_, rank, world).contiguous() for t_ in (qf, kf, vf)), causal=True, zigzag=True)
+        o_full, lse_full = fab.attention(qf, kf, vf, causal=True, return_lse=True)
+        err = (o_r.float() - fab.zigzag_shard(o_full, rank, world).float()).abs().max()
+        err_l = (lse_r - fab.zigzag_shard(lse_full.unsqueeze(-1), rank, world).squeeze(-1)).abs().max()
+        t = torch.stack([err, err_l])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out.append({"check": f"zigzag_causal_ring_vs_single_gpu dtype={str(dtype).split('.')[-1]} d={dd} N={Nf}", "world": world,
+                    "max_err_o": float(t[0]), "max_err_lse": float(t[1]), "ok": bool(t[0] < tol and t[1] < 2e-3)})
 
     # ---- 3. C5-shaped ring timing ----
     Hh, dd, n_loc = args.heads, 128, args.n_per_rank
@@ -99,6 +120,28 @@ def main():
                 "tflops_total": round(flops / float(t[0]) * 1e-9, 1), "tflops_per_gpu": round(flops / float(t[0]) * 1e-9 / world, 1),
                 "ms_compute_only_same_flops": round(float(t_local[0]), 3),
                 "kv_bytes_sent_per_gpu_per_step": 2 * Hh * n_loc * dd * 2})
+    # ---- 4. causal C5-shaped ring: contiguous shards (lopsided: rank P-1 works P times as long as rank 0) vs zig-zag ----
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(args.reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        tt = torch.tensor([best], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt[0])
+
+    t_plain = timed(lambda: fab.ring_attention(qs, ks, vs, causal=True))
+    t_zz = timed(lambda: fab.ring_attention(qs, ks, vs, causal=True, zigzag=True))
+    out.append({"check": f"causal_ring_timing H={Hh} d={dd} bf16 N={n_total}", "world": world, "ms_contiguous_shards": round(t_plain, 3),
+                "ms_zigzag": round(t_zz, 3), "tflops_total_zigzag": round(flops / 2 / t_zz * 1e-9, 1),
+                "tflops_per_gpu_zigzag": round(flops / 2 / t_zz * 1e-9 / world, 1)})
     if rank == 0:
         for o in out:
             print(json.dumps(o), flush=True)

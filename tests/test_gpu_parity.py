@@ -168,6 +168,23 @@ def test_cross_lengths(fab, oracle, cuda_device, nq, nk, causal):
     assert np.abs(lse - lse_ref).max() < 5e-3
 
 
+@pytest.mark.parametrize("dtype,d", [(torch.float32, 64), (torch.bfloat16, 128)])
+def test_batch_invariant_flag(fab, cuda_device, dtype, d):
+    """FA_FLAG_BATCH_INVARIANT: a (batch, head) slice is bit-identical alone, in a larger launch and in a B x H shard (the item
+    list of a launch — whole waves of 256-row items plus a split-KV remainder wave — depends on the launch size otherwise)."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    bh, n = 40, 1024       # 160 256-row blocks: one whole wave of 148 + a 12-block remainder that runs as split-KV items by default
+    q, k, v = (torch.randn(bh, n, d, generator=g).to(dtype).to(cuda_device) for _ in range(3))
+    o_all = fab.attention(q, k, v, causal=True, batch_invariant=True)
+    assert fab.last_impl() == fab.FA_IMPL_TCGEN05
+    for sl in (slice(0, 1), slice(37, 40), slice(0, 20), slice(20, 40)):
+        o_sl = fab.attention(q[sl].contiguous(), k[sl].contiguous(), v[sl].contiguous(), causal=True, batch_invariant=True)
+        assert torch.equal(o_sl, o_all[sl])
+    o_def = fab.attention(q, k, v, causal=True)
+    tol = TOL_BF16 if dtype == torch.bfloat16 else TOL_TF32_FEWKEYS
+    assert float((o_def.float() - o_all.float()).abs().max()) < tol
+
+
 def test_four_d_and_three_d_inputs_agree(fab, cuda_device):
     q = torch.randn(2, 4, 256, 64, device=cuda_device)
     k, v = torch.randn_like(q), torch.randn_like(q)
@@ -257,6 +274,51 @@ def test_merge_partials_and_single_gpu_ring_emulation(fab, oracle, cuda_device):
     assert o_bf.dtype == torch.bfloat16 and np.abs(o_bf.float().cpu().numpy() - o_ref).max() < TOL_BF16
 
 
+@pytest.mark.parametrize("dtype,d", [(torch.float32, 64), (torch.bfloat16, 128)])
+def test_strided_views_are_read_in_place(fab, cuda_device, dtype, d):
+    """A slice of the sequence axis (strides != shape) goes into the TMA tensor maps as it is: same bits as the
+    contiguous copy, for Q and for K/V, causal with n_q != n_k included."""
+    g = torch.Generator(device="cpu").manual_seed(9)
+    q, k, v = (torch.randn(2, 3, 512, d, generator=g).to(dtype).to(cuda_device) for _ in range(3))
+    qs, ks, vs = q[:, :, 128:384], k[:, :, :256], v[:, :, :256]
+    assert not qs.is_contiguous()
+    for causal in (False, True):
+        o_view, lse_view = fab.attention(qs, ks, vs, causal=causal, return_lse=True)
+        assert fab.last_impl() == fab.FA_IMPL_TCGEN05
+        o_copy, lse_copy = fab.attention(qs.contiguous(), ks.contiguous(), vs.contiguous(), causal=causal, return_lse=True)
+        assert torch.equal(o_view, o_copy) and torch.equal(lse_view, lse_copy)
+    o_view = fab.attention(q[:, :, 256:], k, v, causal=True, batch_invariant=True)   # bottom-right aligned causal, n_q = 256, n_k = 512
+    assert torch.equal(o_view, fab.attention(q, k, v, causal=True, batch_invariant=True)[:, :, 256:])
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_zigzag_causal_ring_emulated_on_one_gpu(fab, oracle, cuda_device, P):
+    """The arithmetic of the balanced causal ring without the transport: every 'rank' runs its zig-zag step plan
+    (strided half-shard views, cross-length causal calls, two accumulators, fa_merge_partials) on ONE GPU; the
+    reassembled result must equal the unpartitioned causal forward."""
+    B, H, N, d = 1, 2, 256 * 2 * P, 128
+    q, k, v = (_bf16_round(seeded((B, H, N, d), s)) for s in (121, 122, 123))
+    tq, tk, tv = (torch.from_numpy(x).cuda().to(torch.bfloat16) for x in (q, k, v))
+    shards = [[fab.zigzag_shard(t, r, P).contiguous() for t in (tq, tk, tv)] for r in range(P)]
+    c = N // (2 * P)
+    outs = []
+    for r in range(P):
+        acc = [None, None]
+        for _, src in fab.ring.ring_schedule(r, P):
+            for half, keys, causal in fab.zigzag_step_plan(r, src):
+                q_h = shards[r][0][..., half * c:(half + 1) * c, :]
+                k_s, v_s = (shards[src][1], shards[src][2]) if keys == "all" else (shards[src][1][..., :c, :], shards[src][2][..., :c, :])
+                o_s, lse_s = fab.attention(q_h, k_s, v_s, causal=causal, return_lse=True, out_f32=True)
+                if acc[half] is None:
+                    acc[half] = (o_s, lse_s)
+                else:
+                    fab.merge_partials(acc[half][0], acc[half][1], o_s, lse_s)
+        outs.append(torch.cat([acc[0][0], acc[1][0]], dim=-2))
+    o = fab.zigzag_unshard(outs, P).cpu().numpy()
+    o_ref, _ = oracle.f64(q, k, v, 1 / math.sqrt(d), True)
+    assert np.abs(o - o_ref).max() < 5e-3
+
+
 # ------------------------------------------------------------------ size-independent properties at BASELINE sizes
 @pytest.mark.parametrize("name,B,H,N,d,dtype", [("C2", 2, 8, 8192, 64, torch.float32), ("C3", 8, 16, 1024, 32, torch.float32),
                                                  ("C4", 4, 32, 8192, 128, torch.bfloat16)])
@@ -317,9 +379,12 @@ def test_multi_gpu_sharding_and_ring_over_nccl(cuda_device):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
-    assert lines[0]["bitwise_equal"]
+    assert lines[0]["bitwise_equal"]                           # FA_FLAG_BATCH_INVARIANT: sharded == unsharded, bit for bit
+    assert lines[0]["default_mode_max_abs_diff"] < 2e-2        # default scheduling: within the bf16 tolerance
     ring = [l for l in lines if l["check"].startswith("ring_vs_single_gpu")]
     assert len(ring) == 4 and all(l["ok"] for l in ring), ring
+    zz = [l for l in lines if l["check"].startswith("zigzag_causal_ring_vs_single_gpu")]
+    assert len(zz) == 2 and all(l["ok"] for l in zz), zz
 
 
 def test_cuda_graph_capture_and_replay(fab, cuda_device):

@@ -36,6 +36,76 @@ def _oracle_attn(scale):
     return attn, merge
 
 
+def _zigzag_worker(rank, world, port, ret):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import flashattention_c_b200 as fab
+        from oracle import fa_oracle
+
+        B, H, N, d = 1, 2, 16 * 2 * world, 16
+        rng = np.random.default_rng(200)
+        q, k, v = (torch.from_numpy(rng.standard_normal((B, H, N, d), dtype=np.float32)) for _ in range(3))
+        scale = 0.25
+        attn, merge = _oracle_attn(scale)
+        qs, ks, vs = (fab.zigzag_shard(t, rank, world).contiguous() for t in (q, k, v))
+        o_loc, lse_loc = fab.ring_attention(qs, ks, vs, causal=True, scale=scale, zigzag=True, _attn=attn, _merge=merge,
+                                            _finalize=lambda o: o)
+        o_full, lse_full = fa_oracle.f64(q.numpy(), k.numpy(), v.numpy(), scale, True)
+        o_ref = fab.zigzag_shard(torch.from_numpy(o_full), rank, world).numpy()
+        lse_ref = fab.zigzag_shard(torch.from_numpy(lse_full).unsqueeze(-1), rank, world).squeeze(-1).numpy()
+        # all ranks' shards put back together give the full-sequence result
+        gathered = [torch.empty_like(o_loc) for _ in range(world)]
+        dist.all_gather(gathered, o_loc.contiguous())
+        err_full = float(np.abs(fab.zigzag_unshard(gathered, world).numpy() - o_full).max())
+        ret[rank] = (float(np.abs(o_loc.numpy() - o_ref).max()), float(np.abs(lse_loc.numpy() - lse_ref).max()), err_full)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_zigzag_causal_ring_over_gloo(world):
+    """Balanced causal ring: rank r holds chunks r and 2P-1-r; rotation, per-step plan and the two-accumulator merge."""
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_zigzag_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for rank in range(world):
+        err_o, err_l, err_full = ret[rank]
+        assert err_o < 1e-12 and err_l < 1e-12 and err_full < 1e-12, (rank, err_o, err_l, err_full)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_zigzag_plan_covers_the_causal_mask_exactly_and_is_balanced(world):
+    """Host logic only: over all ring steps the plan of every rank visits each visible (query, key) pair exactly once and
+    no masked pair, and every step of every rank costs the same number of pairs."""
+    sys.path.insert(0, str(ROOT))
+    import flashattention_c_b200 as fab
+
+    c = 4
+    n = 2 * world * c
+    pos = [list(range(r * c, (r + 1) * c)) + list(range((2 * world - 1 - r) * c, (2 * world - r) * c)) for r in range(world)]
+    for rank in range(world):
+        seen = np.zeros((n, n), dtype=np.int64)
+        for _, src in fab.ring.ring_schedule(rank, world):
+            pairs = 0
+            for half, keys, causal in fab.zigzag_step_plan(rank, src):
+                qpos = pos[rank][half * c:(half + 1) * c]
+                kpos = pos[src] if keys == "all" else pos[src][:c]
+                for i, qp in enumerate(qpos):
+                    for j, kp in enumerate(kpos):
+                        if causal and j > i + (len(kpos) - len(qpos)):
+                            continue
+                        seen[qp, kp] += 1
+                        pairs += 1
+            assert pairs in (2 * c * c, c * (c + 1) // 2 + c * c + c * (c + 1) // 2), (rank, src, pairs)
+        for qp in pos[rank]:
+            expect = (np.arange(n) <= qp).astype(np.int64)
+            assert (seen[qp] == expect).all(), (rank, qp)
+
+
 def _worker(rank, world, port, causal, ret):
     sys.path.insert(0, str(ROOT))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
