@@ -569,7 +569,13 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           const int iv = r0 + 2 * j + 1, ik = r0 + 2 * j + 2;
           const int vbuf = iv % T::kNBuf, kbuf = ik % T::kNBuf;
           wait_full(iv);
+#if FA_TRACE
+          FA_TRACE_AT(2, steps_a, 5);      // V_j landed
+#endif
           if (j + 1 < w.n_max) wait_full(ik);
+#if FA_TRACE
+          FA_TRACE_AT(3, steps_a, 5);      // K_(j+1) landed
+#endif
           tc_fence_after();
 #if FA_TRACE
           FA_TRACE_AT(2, steps_a, 7);      // K/V of this step landed (slot 0 of the same row = step start)

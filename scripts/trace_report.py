@@ -39,6 +39,9 @@ def main(path, lo=8, hi=40):
     if (r[3, lo:hi, 7] >= 0).all() and (r[2, lo + 1:hi + 1, 7] >= 0).all():
         print(f"MMA warp: B step end -> slots released {np.mean(r[3, lo:hi, 7] - r[3, lo:hi, 6]):6.0f} | released -> next K/V landed "
               f"{np.mean(r[2, lo + 1:hi + 1, 7] - r[3, lo:hi, 7]):6.0f} | landed -> A step start {np.mean(r[2, lo + 1:hi + 1, 0] - r[2, lo + 1:hi + 1, 7]):6.0f}")
+        if (r[2, lo + 1:hi + 1, 5] >= 0).all() and (r[3, lo + 1:hi + 1, 5] >= 0).all():
+            print(f"MMA warp: released -> V_j wait done {np.mean(r[2, lo + 1:hi + 1, 5] - r[3, lo:hi, 7]):6.0f} | -> K_(j+1) wait done "
+                  f"{np.mean(r[3, lo + 1:hi + 1, 5] - r[2, lo + 1:hi + 1, 5]):6.0f} | -> fence done {np.mean(r[2, lo + 1:hi + 1, 7] - r[3, lo + 1:hi + 1, 5]):6.0f}")
         print(f"MMA warp: A step end -> B step start {np.mean(r[3, lo:hi, 0] - r[2, lo:hi, 6]):6.0f} | A step {np.mean(r[2, lo:hi, 6] - r[2, lo:hi, 0]):6.0f} | B step {np.mean(r[3, lo:hi, 6] - r[3, lo:hi, 0]):6.0f}")
     # producer: TMA issue time of K_j (role 2 slot 4, row j) / V_j (role 3 slot 4, row j) vs the MMA warp seeing V_j and K_{j+1}
     # landed (role 2 slot 7, row j)
