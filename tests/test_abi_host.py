@@ -3,6 +3,7 @@ argument validation works without a device, and the host-side logic (sharding, r
 import ctypes
 import re
 import subprocess
+import sys
 from pathlib import Path
 
 import pytest
@@ -34,6 +35,49 @@ def test_library_loads_and_exports_every_declared_symbol(fab):
                         capture_output=True, text=True, check=True).stdout
     for name in _declared_symbols():
         assert re.search(rf"\bT {name}\b", nm), f"{name} is not an unmangled (extern \"C\") export"
+
+
+def test_ctypes_struct_layout_matches_the_header(tmp_path):
+    """fa_params as gcc lays it out from include/fa_b200.h == the ctypes mirror (sizes and every field offset), and the
+    flag / enum values the Python side hard-codes are the header's."""
+    import ctypes
+    import subprocess
+
+    sys.path.insert(0, str(ROOT))
+    from flashattention_c_b200 import _lib
+
+    fields = [f[0] for f in _lib.FaParams._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "fa_b200.h"}"', 'int main(void) {',
+            '  printf("%zu\\n", sizeof(fa_params));']
+    prog += [f'  printf("%zu\\n", offsetof(fa_params, {f}));' for f in fields]
+    prog += ['  printf("%d %d %d %d %d %d\\n", FA_F32, FA_BF16, FA_IMPL_TCGEN05, FA_IMPL_SIMT, FA_FLAG_BATCH_INVARIANT, FA_B200_VERSION);',
+             '  return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == ctypes.sizeof(_lib.FaParams)
+    for f, off in zip(fields, out[1:1 + len(fields)]):
+        assert int(off) == getattr(_lib.FaParams, f).offset, f
+    consts = [int(x) for x in out[1 + len(fields):]]
+    assert consts[:5] == [_lib.FA_F32, _lib.FA_BF16, _lib.FA_IMPL_TCGEN05, _lib.FA_IMPL_SIMT, _lib.FA_FLAG_BATCH_INVARIANT]
+
+
+def test_tma_view_passes_aligned_strided_views_and_copies_the_rest():
+    """Host logic of api.attention: which views go to the kernel as they are (strides into the TMA map) and which are copied."""
+    import torch
+
+    sys.path.insert(0, str(ROOT))
+    from flashattention_c_b200 import api
+
+    x = torch.zeros(2, 3, 64, 32)
+    v = x[:, :, 16:48]                      # sequence slice: last axis contiguous, strides multiples of 16 bytes
+    assert api._tma_view(v) is v and api._strides_bhn(v) == (3 * 64 * 32, 64 * 32, 32)
+    assert api._tma_view(x.transpose(2, 3)).is_contiguous()          # last axis strided -> copy
+    assert api._tma_view(x[..., 1:31]).is_contiguous() and api._tma_view(x[..., 1:31]) is not x   # misaligned base -> copy
+    y3 = torch.zeros(6, 64, 32)[:, 8:40]
+    assert api._strides_bhn(y3) == (6 * 64 * 32, 64 * 32, 32)
 
 
 def test_version_and_strerror(fab):
