@@ -10,7 +10,7 @@ Host-side mirror of the reference interface (names, argument meaning, error beha
 Everything runs on hand-written sm_100a kernels through the C-ABI library libfa_b200.so
 (include/fa_b200.h).  There is no CPU or eager-PyTorch fallback: without the library or a B200 the calls raise.
 """
-from ._lib import FA_BF16, FA_F32, FA_FLAG_BATCH_INVARIANT, FA_IMPL_AUTO, FA_IMPL_SIMT, FA_IMPL_TCGEN05, FaError, lib  # noqa: F401
+from ._lib import FA_BF16, FA_F16, FA_F32, FA_FLAG_BATCH_INVARIANT, FA_IMPL_AUTO, FA_IMPL_SIMT, FA_IMPL_TCGEN05, FaError, lib  # noqa: F401
 from .api import (  # noqa: F401
     attention,
     attention_forward,

@@ -11,7 +11,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import FA_BF16, FA_F32, FaError, FaParams, check, lib
+from ._lib import FA_BF16, FA_F16, FA_F32, FaError, FaParams, check, lib
 
 
 def _dtype_code(t: torch.Tensor) -> int:
@@ -19,7 +19,9 @@ def _dtype_code(t: torch.Tensor) -> int:
         return FA_F32
     if t.dtype == torch.bfloat16:
         return FA_BF16
-    raise FaError(f"unsupported dtype {t.dtype}: only float32 (tf32 tensor cores) and bfloat16")
+    if t.dtype == torch.float16:
+        return FA_F16
+    raise FaError(f"unsupported dtype {t.dtype}: only float32 (tf32 tensor cores), bfloat16 and float16")
 
 
 def _stream_ptr(device) -> int:
@@ -66,7 +68,7 @@ def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False
               batch_invariant=False):
     """O = softmax(scale * Q K^T [+ causal mask]) V.   scale defaults to 1/sqrt(d).
 
-    Q, K, V: CUDA tensors [B*H, N, d] or [B, H, N, d], float32 or bfloat16; strided views with a contiguous last axis
+    Q, K, V: CUDA tensors [B*H, N, d] or [B, H, N, d], float32, bfloat16 or float16; strided views with a contiguous last axis
     (e.g. a slice of the sequence axis) are read in place.
     Returns O (same shape/dtype as Q; float32 if out_f32) and, if return_lse, LSE float32 [..., N].
     batch_invariant: FA_FLAG_BATCH_INVARIANT — a (batch, head) slice gives bit-identical results whatever else is in the
@@ -88,7 +90,7 @@ def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False
         p.batch, p.heads, p.n_q, p.n_k, p.head_dim = b, h, nq, nk, d
         p.dtype = _dtype_code(Q)
         p.causal = 1 if causal else 0
-        p.o_f32 = 1 if (out_f32 and Q.dtype == torch.bfloat16) else 0
+        p.o_f32 = 1 if (out_f32 and Q.dtype != torch.float32) else 0
         p.scale = float(scale)
         (p.q_stride_b, p.q_stride_h, p.q_stride_n) = _strides_bhn(Q)
         (p.k_stride_b, p.k_stride_h, p.k_stride_n) = _strides_bhn(K)
@@ -170,13 +172,18 @@ def merge_partials(o_acc, lse_acc, o_new, lse_new):
     return o_acc, lse_acc
 
 
-def cast_to_bf16(src, dst=None):
+def cast_to_16(src, dtype, dst=None):
+    """fp32 -> bfloat16 / float16 on the current stream (the final cast of the ring accumulator)."""
     if dst is None:
-        dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+        dst = torch.empty(src.shape, dtype=dtype, device=src.device)
     with torch.cuda.device(src.device):
-        check(lib().fa_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), ctypes.c_void_p(_stream_ptr(src.device))),
-              "fa_cast_f32_to_bf16")
+        check(lib().fa_cast_f32(src.data_ptr(), dst.data_ptr(), src.numel(), _dtype_code(dst), ctypes.c_void_p(_stream_ptr(src.device))),
+              "fa_cast_f32")
     return dst
+
+
+def cast_to_bf16(src, dst=None):
+    return cast_to_16(src, torch.bfloat16, dst)
 
 
 def last_impl() -> int:

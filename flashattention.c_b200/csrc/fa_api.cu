@@ -4,6 +4,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -150,10 +151,13 @@ constexpr int kMapCacheSize = 32;
 struct MapCache { MapKey key[kMapCacheSize]; CUtensorMap map[kMapCacheSize]; int used = 0; int next = 0; };
 thread_local MapCache t_map_cache;
 
-int make_map(CUtensorMap* out, const void* ptr, int elem_size, bool is_bf16, int64_t batch, int64_t heads, int64_t n, int d,
+// `elem` is the fa_dtype of the tensor's elements.  The box is always 128 bytes of d wide: a head dim that does not fill
+// its last box (or is smaller than one box) is zero-filled on load and clipped on store by TMA.
+int make_map(CUtensorMap* out, const void* ptr, int elem_size, int elem, int64_t batch, int64_t heads, int64_t n, int d,
              int64_t sb, int64_t sh, int64_t sn, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, bool tf32_convert = false) {
-  CUtensorMapDataType dt = is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  if (!is_bf16 && tf32_convert) dt = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;  // TMA converts fp32 -> tf32 while loading
+  CUtensorMapDataType dt = elem == FA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                         : elem == FA_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  if (elem == FA_F32 && tf32_convert) dt = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;  // TMA converts fp32 -> tf32 while loading
   const MapKey key{ptr, elem_size, (int)dt, (int)swizzle, d, batch, heads, n, sb, sh, sn};
   MapCache& mc = t_map_cache;
   for (int i = 0; i < mc.used; ++i)
@@ -187,11 +191,11 @@ int make_map(CUtensorMap* out, const void* ptr, int elem_size, bool is_bf16, int
   return FA_OK;
 }
 
-template <bool kTF32, int kHeadDim, bool kCausal, bool kOutF32>
+template <bool kTF32, int kHeadDim, bool kCausal, bool kOutF32, bool kF16>
 int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo, const fa::FwdParams& fp,
               cudaStream_t st) {
   using T = fa::FwdTraits<kTF32, kHeadDim, kOutF32>;
-  auto kern = fa::fa_fwd_sm100_kernel<kTF32, kHeadDim, kCausal, kOutF32>;
+  auto kern = fa::fa_fwd_sm100_kernel<kTF32, kHeadDim, kCausal, kOutF32, kF16>;
   static bool attr_set[64] = {};  // per kernel instance and per device (the attribute is per device); benign race (idempotent)
   int dev = 0;
   FA_CUDA(cudaGetDevice(&dev));
@@ -209,20 +213,27 @@ int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& m
   return FA_OK;
 }
 
-template <bool kTF32, int kHeadDim, bool kOutF32>
+template <bool kTF32, int kHeadDim, bool kOutF32, bool kF16 = false>
 int launch_tc_c(bool causal, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
                 const fa::FwdParams& fp, cudaStream_t st) {
-  return causal ? launch_tc<kTF32, kHeadDim, true, kOutF32>(mq, mk, mv, mo, fp, st)
-                : launch_tc<kTF32, kHeadDim, false, kOutF32>(mq, mk, mv, mo, fp, st);
+  return causal ? launch_tc<kTF32, kHeadDim, true, kOutF32, kF16>(mq, mk, mv, mo, fp, st)
+                : launch_tc<kTF32, kHeadDim, false, kOutF32, kF16>(mq, mk, mv, mo, fp, st);
 }
 
-bool tc_supported(const fa_params* p) {
-  if (p->dtype == FA_F32) return p->head_dim == 32 || p->head_dim == 64;
-  return p->head_dim == 64 || p->head_dim == 128;
+// The tcgen05 kernel is instantiated for tile rows of 128 and 256 bytes: fp32 head dims 32 / 64, 16-bit head dims 64 / 128.
+// Any smaller head dim whose rows keep TMA's 16-byte alignment runs on the next instance up: TMA zero-fills the missing
+// columns of Q, K and V in SMEM (zero columns add nothing to q.k, and give zero O columns) and clips them from the O store.
+// 0 = no instance (fp32 d > 64, 16-bit d > 128: CUDA-core kernel).
+int tc_instance_dim(const fa_params* p) {
+  const int d = p->head_dim;
+  if (p->dtype == FA_F32) return (d % 4 || d > 64) ? 0 : (d <= 32 ? 32 : 64);
+  return (d % 8 || d > 128) ? 0 : (d <= 64 ? 64 : 128);
 }
+bool tc_supported(const fa_params* p) { return tc_instance_dim(p) != 0; }
 
 int run_tc(const fa_params* p, cudaStream_t st) {
-  const bool bf16 = p->dtype == FA_BF16;
+  const bool bf16 = p->dtype != FA_F32;   // 16-bit operands (bf16 or fp16): kind::f16 instances
+  const int in_dt = p->dtype;
   const int in_sz = bf16 ? 2 : 4;
   const bool out_f32 = !bf16 || p->o_f32;
   const int out_sz = out_f32 ? 4 : 2;
@@ -231,8 +242,8 @@ int run_tc(const fa_params* p, cudaStream_t st) {
   // fp32 tensors are loaded through TFLOAT32 tensor maps: TMA rounds fp32 -> tf32 to nearest on the way into SMEM, which
   // removes the truncation bias the tensor core would otherwise apply (measured on B200: max error 4.1e-4 -> 9.8e-5 on C1).
   static const bool tf32_tma = [] { const char* e = getenv("FA_B200_TMA_TF32"); return !(e && atoi(e) == 0); }();
-  if ((rc = make_map(&mq, p->q, in_sz, bf16, p->batch, p->heads, p->n_q, p->head_dim, p->q_stride_b, p->q_stride_h, p->q_stride_n, CU_TENSOR_MAP_SWIZZLE_128B, tf32_tma))) return rc;
-  if ((rc = make_map(&mk, p->k, in_sz, bf16, p->batch, p->heads, p->n_k, p->head_dim, p->k_stride_b, p->k_stride_h, p->k_stride_n, CU_TENSOR_MAP_SWIZZLE_128B, tf32_tma))) return rc;
+  if ((rc = make_map(&mq, p->q, in_sz, in_dt, p->batch, p->heads, p->n_q, p->head_dim, p->q_stride_b, p->q_stride_h, p->q_stride_n, CU_TENSOR_MAP_SWIZZLE_128B, tf32_tma))) return rc;
+  if ((rc = make_map(&mk, p->k, in_sz, in_dt, p->batch, p->heads, p->n_k, p->head_dim, p->k_stride_b, p->k_stride_h, p->k_stride_n, CU_TENSOR_MAP_SWIZZLE_128B, tf32_tma))) return rc;
   // V is the MN-major B operand of P*V: bf16 uses the ordinary 128B swizzle; 32-bit (tf32) MN-major operands must
   // be in the SWIZZLE_128B_BASE32B layout (32-byte units over 4-row groups), written by TMA's 128B_ATOM_32B mode.
   uint32_t v_lbo = fa::kChunkBytes, v_sbo = bf16 ? 1024 : 512, v_layout = bf16 ? fa::kLayoutSw128 : fa::kLayoutSw128Base32;
@@ -243,8 +254,8 @@ int run_tc(const fa_params* p, cudaStream_t st) {
     if (!bf16 && vv == 3) { v_lbo = 512; v_sbo = fa::kChunkBytes; }
     if (!bf16 && vv == 4) { v_layout = fa::kLayoutSw128; v_sbo = 1024; v_swz = CU_TENSOR_MAP_SWIZZLE_128B; }
   }
-  if ((rc = make_map(&mv, p->v, in_sz, bf16, p->batch, p->heads, p->n_k, p->head_dim, p->v_stride_b, p->v_stride_h, p->v_stride_n, v_swz, tf32_tma))) return rc;
-  if ((rc = make_map(&mo, p->o, out_sz, !out_f32, p->batch, p->heads, p->n_q, p->head_dim, p->o_stride_b, p->o_stride_h, p->o_stride_n))) return rc;
+  if ((rc = make_map(&mv, p->v, in_sz, in_dt, p->batch, p->heads, p->n_k, p->head_dim, p->v_stride_b, p->v_stride_h, p->v_stride_n, v_swz, tf32_tma))) return rc;
+  if ((rc = make_map(&mo, p->o, out_sz, out_f32 ? (int)FA_F32 : in_dt, p->batch, p->heads, p->n_q, p->head_dim, p->o_stride_b, p->o_stride_h, p->o_stride_n))) return rc;
   fa::FwdParams fp;
   fp.scale = p->scale;
   fp.scale_log2 = p->scale * 1.4426950408889634f;
@@ -302,15 +313,17 @@ int run_tc(const fa_params* p, cudaStream_t st) {
   } trace_dump{trace_path, d_trace, trace_n, st};
 #endif
   const bool c = p->causal != 0;
+  const int di = tc_instance_dim(p);   // kernel instance (>= head_dim; the tensor maps carry the true head dim)
+  const bool f16 = p->dtype == FA_F16;
   if (!bf16) {
-    if (p->head_dim == 32) return launch_tc_c<true, 32, false>(c, mq, mk, mv, mo, fp, st);
-    if (p->head_dim == 64) return launch_tc_c<true, 64, false>(c, mq, mk, mv, mo, fp, st);
+    if (di == 32) return launch_tc_c<true, 32, false>(c, mq, mk, mv, mo, fp, st);
+    if (di == 64) return launch_tc_c<true, 64, false>(c, mq, mk, mv, mo, fp, st);
   } else if (!p->o_f32) {
-    if (p->head_dim == 64) return launch_tc_c<false, 64, false>(c, mq, mk, mv, mo, fp, st);
-    if (p->head_dim == 128) return launch_tc_c<false, 128, false>(c, mq, mk, mv, mo, fp, st);
+    if (di == 64) return f16 ? launch_tc_c<false, 64, false, true>(c, mq, mk, mv, mo, fp, st) : launch_tc_c<false, 64, false>(c, mq, mk, mv, mo, fp, st);
+    if (di == 128) return f16 ? launch_tc_c<false, 128, false, true>(c, mq, mk, mv, mo, fp, st) : launch_tc_c<false, 128, false>(c, mq, mk, mv, mo, fp, st);
   } else {
-    if (p->head_dim == 64) return launch_tc_c<false, 64, true>(c, mq, mk, mv, mo, fp, st);
-    if (p->head_dim == 128) return launch_tc_c<false, 128, true>(c, mq, mk, mv, mo, fp, st);
+    if (di == 64) return f16 ? launch_tc_c<false, 64, true, true>(c, mq, mk, mv, mo, fp, st) : launch_tc_c<false, 64, true>(c, mq, mk, mv, mo, fp, st);
+    if (di == 128) return f16 ? launch_tc_c<false, 128, true, true>(c, mq, mk, mv, mo, fp, st) : launch_tc_c<false, 128, true>(c, mq, mk, mv, mo, fp, st);
   }
   return FA_ERR_UNSUPPORTED;
 }
@@ -339,6 +352,7 @@ int run_simt(const fa_params* p, cudaStream_t st) {
   sp.n_q = (int)p->n_q; sp.n_k = (int)p->n_k; sp.heads = (int)p->heads; sp.batch = (int)p->batch; sp.head_dim = p->head_dim;
   sp.causal = p->causal; sp.causal_offset = (int)(p->n_k - p->n_q); sp.scale = p->scale;
   if (p->dtype == FA_F32) return launch_simt<float, float>(sp, st);
+  if (p->dtype == FA_F16) return p->o_f32 ? launch_simt<__half, float>(sp, st) : launch_simt<__half, __half>(sp, st);
   if (p->o_f32) return launch_simt<__nv_bfloat16, float>(sp, st);
   return launch_simt<__nv_bfloat16, __nv_bfloat16>(sp, st);
 }
@@ -395,10 +409,10 @@ const char* fa_strerror(int status) {
 int fa_forward_ex(const fa_params* p, void* stream) {
   if (!p || !p->q || !p->k || !p->v || !p->o) return FA_ERR_INVALID_ARG;
   if (p->batch <= 0 || p->heads <= 0 || p->n_q <= 0 || p->n_k <= 0 || p->head_dim <= 0) return FA_ERR_INVALID_ARG;
-  if (p->dtype != FA_F32 && p->dtype != FA_BF16) return FA_ERR_INVALID_ARG;
+  if (p->dtype != FA_F32 && p->dtype != FA_BF16 && p->dtype != FA_F16) return FA_ERR_INVALID_ARG;
   if (!(p->scale > 0.f) || !std::isfinite(p->scale)) return FA_ERR_INVALID_ARG;
   if (p->n_q > 0x7fffffff || p->n_k > 0x7fffffff || p->batch > 0x7fffffff || p->heads > 0x7fffffff) return FA_ERR_INVALID_ARG;
-  if (p->o_f32 && p->dtype != FA_BF16) return FA_ERR_INVALID_ARG;
+  if (p->o_f32 && p->dtype == FA_F32) return FA_ERR_INVALID_ARG;   // fp32 inputs already give fp32 O
   int major = 0;
   int rc = probe_device(&major);
   if (rc) return rc;
@@ -444,11 +458,11 @@ int fa_forward_host(const void* qh, const void* kh, const void* vh, void* oh, in
                     int32_t head_dim, float scale, int32_t causal, int32_t dtype) {
   if (!qh || !kh || !vh || !oh) return FA_ERR_INVALID_ARG;
   if (batch <= 0 || heads <= 0 || n_q <= 0 || n_k <= 0 || head_dim <= 0) return FA_ERR_INVALID_ARG;
-  if (dtype != FA_F32 && dtype != FA_BF16) return FA_ERR_INVALID_ARG;
+  if (dtype != FA_F32 && dtype != FA_BF16 && dtype != FA_F16) return FA_ERR_INVALID_ARG;
   int major = 0;
   int rc = probe_device(&major);
   if (rc) return rc;
-  const size_t es = dtype == FA_BF16 ? 2 : 4;
+  const size_t es = dtype == FA_F32 ? 4 : 2;
   const size_t bq = (size_t)batch * heads * n_q * head_dim * es, bkv = (size_t)batch * heads * n_k * head_dim * es;
   std::lock_guard<std::mutex> lk(g_hs_mu);
   HostScratch& s = g_hs;
@@ -559,18 +573,21 @@ int fa_merge_partials(float* o_acc, float* lse_acc, const float* o_new, const fl
   return FA_OK;
 }
 
-int fa_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
-  if (!src || !dst || n <= 0) return FA_ERR_INVALID_ARG;
+int fa_cast_f32(const float* src, void* dst, int64_t n, int32_t dtype, void* stream) {
+  if (!src || !dst || n <= 0 || (dtype != FA_BF16 && dtype != FA_F16)) return FA_ERR_INVALID_ARG;
   int major = 0;
   int rc = probe_device(&major);
   if (rc) return rc;
   const int64_t threads = (n + 3) / 4;
-  fa::fa_cast_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, static_cast<__nv_bfloat16*>(dst), n);
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == FA_BF16) fa::fa_cast_16_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+  else fa::fa_cast_16_kernel<__half><<<grid, 256, 0, st>>>(src, static_cast<__half*>(dst), n);
   FA_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return FA_OK;
 }
+int fa_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) { return fa_cast_f32(src, dst, n, FA_BF16, stream); }
 
 // ------------------------------ reference-named shims ------------------------------
 static void die_on(int rc, const char* where) {

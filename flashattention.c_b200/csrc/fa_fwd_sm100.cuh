@@ -224,7 +224,9 @@ FA_DEVINL Item decode_item(const FwdParams& p, int bid) {
   return it;
 }
 
-template <bool kTF32, int kHeadDim, bool kCausal, bool kOutF32>
+// kF16 (16-bit instances only): the operands are IEEE fp16 instead of bf16 — same kind::f16 instruction, operand format 0
+// instead of 1; P <= 2^kRescaleThreshold by construction (lazy rescale), far inside the fp16 range.
+template <bool kTF32, int kHeadDim, bool kCausal, bool kOutF32, bool kF16 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
@@ -407,7 +409,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   } else if (warp == 9) {
     // =========================== MMA issuer ===========================
     // The whole warp follows the (warp-uniform) control flow and waits on the mbarriers; one elected lane issues.
-    constexpr uint32_t kFmt = kTF32 ? 2u : 1u;
+    constexpr uint32_t kFmt = kTF32 ? 2u : (kF16 ? 0u : 1u);   // tf32 / fp16 / bf16 operands
     constexpr uint32_t idesc_s = make_idesc(kFmt, 0, kBlockM, kBlockN);
     constexpr uint32_t idesc_pv = make_idesc(kFmt, 1, kBlockM, kHeadDim);
     // K-major operands (Q, K): LBO unused for swizzled K-major (encoded 1), SBO = 1024 B between 8-row groups
@@ -803,7 +805,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             } else {
               uint32_t pk[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(s[cc * 32 + 2 * i], s[cc * 32 + 2 * i + 1]);
+              for (int i = 0; i < 16; ++i) pk[i] = pack_16x2<kF16>(s[cc * 32 + 2 * i], s[cc * 32 + 2 * i + 1]);
               tmem_st16(own ? tP1 + (cc - kChunks0) * 16 : tS + cc * 16, pk);
             }
           }
@@ -922,10 +924,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 for (int g = 0; g < 4; ++g) {
                   const uint32_t chunk16 = static_cast<uint32_t>(half * 4 + g);
                   st_shared_v4(base + ((chunk16 ^ sw) << 4),
-                               pack_bf16x2(__uint_as_float(o[8 * g]), __uint_as_float(o[8 * g + 1])),
-                               pack_bf16x2(__uint_as_float(o[8 * g + 2]), __uint_as_float(o[8 * g + 3])),
-                               pack_bf16x2(__uint_as_float(o[8 * g + 4]), __uint_as_float(o[8 * g + 5])),
-                               pack_bf16x2(__uint_as_float(o[8 * g + 6]), __uint_as_float(o[8 * g + 7])));
+                               pack_16x2<kF16>(__uint_as_float(o[8 * g]), __uint_as_float(o[8 * g + 1])),
+                               pack_16x2<kF16>(__uint_as_float(o[8 * g + 2]), __uint_as_float(o[8 * g + 3])),
+                               pack_16x2<kF16>(__uint_as_float(o[8 * g + 4]), __uint_as_float(o[8 * g + 5])),
+                               pack_16x2<kF16>(__uint_as_float(o[8 * g + 6]), __uint_as_float(o[8 * g + 7])));
                 }
               }
             }

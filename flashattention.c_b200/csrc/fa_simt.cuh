@@ -10,6 +10,7 @@
 // (README.md:31; its serial loop is src/flashattention.cu:265-274).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -26,7 +27,9 @@ struct SimtParams {
 template <typename T> __device__ __forceinline__ float ld_as_float(const T* p);
 template <> __device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p; }
 template <> __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <> __device__ __forceinline__ float ld_as_float<__half>(const __half* p) { return __half2float(*p); }
 template <typename T> __device__ __forceinline__ void st_from_float(T* p, float x);
+template <> __device__ __forceinline__ void st_from_float<__half>(__half* p, float x) { *p = __float2half_rn(x); }
 template <> __device__ __forceinline__ void st_from_float<float>(float* p, float x) { *p = x; }
 template <> __device__ __forceinline__ void st_from_float<__nv_bfloat16>(__nv_bfloat16* p, float x) { *p = __float2bfloat16_rn(x); }
 
@@ -156,15 +159,17 @@ __global__ void fa_merge_lse_kernel(float* __restrict__ lse_acc, const float* __
   lse_acc[row] = (mx == -INFINITY) ? -INFINITY : mx + logf(__expf(la - mx) + __expf(lb - mx));
 }
 
-__global__ void fa_cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+// fp32 -> bf16 / fp16 (final cast of the ring accumulator)
+template <typename T16>
+__global__ void fa_cast_16_kernel(const float* __restrict__ src, T16* __restrict__ dst, int64_t n) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 x = *reinterpret_cast<const float4*>(src + i);
-    __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
-    *reinterpret_cast<__nv_bfloat162*>(dst + i) = lo;
-    *reinterpret_cast<__nv_bfloat162*>(dst + i + 2) = hi;
+    alignas(8) T16 y[4];
+    st_from_float(&y[0], x.x); st_from_float(&y[1], x.y); st_from_float(&y[2], x.z); st_from_float(&y[3], x.w);
+    *reinterpret_cast<uint2*>(dst + i) = *reinterpret_cast<const uint2*>(y);   // one 8-byte store
   } else {
-    for (int64_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+    for (int64_t j = i; j < n; ++j) st_from_float(dst + j, src[j]);
   }
 }
 

@@ -312,6 +312,16 @@ FA_DEVINL uint32_t pack_bf16x2(float lo, float hi) {  // result: low 16 bits = b
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+FA_DEVINL uint32_t pack_f16x2(float lo, float hi) {   // low 16 bits = fp16(lo), high = fp16(hi)
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <bool kF16>
+FA_DEVINL uint32_t pack_16x2(float lo, float hi) {     // the 16-bit operand type of the kind::f16 instances: fp16 or bf16
+  if constexpr (kF16) return pack_f16x2(lo, hi);
+  else return pack_bf16x2(lo, hi);
+}
 FA_DEVINL void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -23,8 +23,8 @@ Shape check_inputs(const torch::Tensor& Q, const torch::Tensor& K, const torch::
   TORCH_CHECK(Q.is_cuda() && K.is_cuda() && V.is_cuda(), "fa_b200.forward: Q, K, V must be CUDA tensors (there is no CPU path)");
   TORCH_CHECK(Q.device() == K.device() && Q.device() == V.device(), "fa_b200.forward: Q, K, V must be on the same device");
   TORCH_CHECK(Q.scalar_type() == K.scalar_type() && Q.scalar_type() == V.scalar_type(), "fa_b200.forward: dtype mismatch");
-  TORCH_CHECK(Q.scalar_type() == torch::kFloat32 || Q.scalar_type() == torch::kBFloat16,
-              "fa_b200.forward: only float32 (tf32 tensor cores) and bfloat16 are supported");
+  TORCH_CHECK(Q.scalar_type() == torch::kFloat32 || Q.scalar_type() == torch::kBFloat16 || Q.scalar_type() == torch::kFloat16,
+              "fa_b200.forward: only float32 (tf32 tensor cores), bfloat16 and float16 are supported");
   TORCH_CHECK(Q.dim() == 3 || Q.dim() == 4, "fa_b200.forward: expected [B*H, N, d] or [B, H, N, d]");
   TORCH_CHECK(K.dim() == Q.dim() && V.dim() == Q.dim(), "fa_b200.forward: rank mismatch");
   TORCH_CHECK(Q.is_contiguous() && K.is_contiguous() && V.is_contiguous(), "fa_b200.forward: tensors must be contiguous");
@@ -53,7 +53,7 @@ std::tuple<torch::Tensor, torch::Tensor> forward_impl(const torch::Tensor& Q, co
     auto opts = Q.options().dtype(torch::kFloat32);
     lse = Q.dim() == 3 ? torch::empty({s.h, s.nq}, opts) : torch::empty({s.b, s.h, s.nq}, opts);
   }
-  const int dtype = Q.scalar_type() == torch::kBFloat16 ? FA_BF16 : FA_F32;
+  const int dtype = Q.scalar_type() == torch::kBFloat16 ? FA_BF16 : (Q.scalar_type() == torch::kFloat16 ? FA_F16 : FA_F32);
   cudaStream_t st = at::cuda::getCurrentCUDAStream();
   const int rc = fa_forward(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), want_lse ? lse.data_ptr<float>() : nullptr, s.b,
                             s.h, s.nq, s.nk, (int)s.d, (float)scale, causal ? 1 : 0, dtype, st);

@@ -136,7 +136,7 @@ def ring_attention(q, k, v, causal=False, scale=None, group=None, zigzag=False, 
 
     if world == 1:
         o, lse = attn(q, k, v, causal)
-        return (_finalize(o) if _finalize else (api.cast_to_bf16(o) if (on_gpu and q.dtype == torch.bfloat16) else o)), lse
+        return (_finalize(o) if _finalize else (api.cast_to_16(o, q.dtype) if (on_gpu and q.dtype != torch.float32) else o)), lse
 
     nxt = dist.get_global_rank(group, (rank + 1) % world) if group is not None else (rank + 1) % world
     prv = dist.get_global_rank(group, (rank - 1) % world) if group is not None else (rank - 1) % world
@@ -183,6 +183,6 @@ def ring_attention(q, k, v, causal=False, scale=None, group=None, zigzag=False, 
         lse_acc = torch.cat([acc[0][1], acc[1][1]], dim=-1)
     if _finalize is not None:
         return _finalize(o_acc), lse_acc
-    if on_gpu and q.dtype == torch.bfloat16:
-        return api.cast_to_bf16(o_acc), lse_acc
+    if on_gpu and q.dtype != torch.float32:
+        return api.cast_to_16(o_acc, q.dtype), lse_acc
     return o_acc, lse_acc

@@ -27,7 +27,8 @@ extern "C" {
 /* element type of Q, K, V (and of O unless stated otherwise) */
 enum fa_dtype {
   FA_F32 = 0,  /* fp32 in HBM, contractions run as tcgen05 kind::tf32 (fp32 accumulate) */
-  FA_BF16 = 1  /* bf16 in HBM, contractions run as tcgen05 kind::f16  (fp32 accumulate) */
+  FA_BF16 = 1, /* bf16 in HBM, contractions run as tcgen05 kind::f16  (fp32 accumulate) */
+  FA_F16 = 2   /* IEEE fp16 in HBM, same kind::f16 instruction with fp16 operands (fp32 accumulate) */
 };
 
 enum fa_status {
@@ -60,10 +61,12 @@ typedef struct fa_params {
   void* o;                 /* same dtype as q unless o_f32 != 0 */
   float* lse;              /* optional [batch, heads, n_q] contiguous fp32; may be NULL */
   int64_t batch, heads, n_q, n_k;
-  int32_t head_dim;        /* tcgen05 path: 32, 64, 128 (bf16: 64, 128); SIMT path: 8..256, %8 == 0 */
+  int32_t head_dim;        /* tcgen05 path: fp32 d <= 64 (d % 4 == 0), bf16 / fp16 d <= 128 (d % 8 == 0) — kernel instances exist
+                              for 128- and 256-byte rows, smaller head dims are zero-padded by TMA; larger ones up to 256
+                              (d % 8 == 0) run on the CUDA-core kernel */
   int32_t dtype;           /* enum fa_dtype */
   int32_t causal;          /* 0 / 1.  Causal is bottom-right aligned: key j visible to row i iff j <= i + (n_k - n_q) */
-  int32_t o_f32;           /* bf16 inputs only: write O as fp32 (used by the ring merge) */
+  int32_t o_f32;           /* bf16 / fp16 inputs only: write O as fp32 (used by the ring merge) */
   float scale;             /* multiplies q.k before the softmax; the reference's torch path uses 1.0f
                               (src/flashattention.cu:593), its llm.c path 1/sqrt(d) (src/llm.c/attention_forward.cu:1123) */
   int64_t q_stride_b, q_stride_h, q_stride_n;
@@ -117,7 +120,9 @@ int fa_forward_host(const void* q_host, const void* k_host, const void* v_host, 
 int fa_merge_partials(float* o_acc, float* lse_acc, const float* o_new, const float* lse_new,
                       int64_t rows, int32_t head_dim, void* stream);
 
-/* fa_cast_f32_to_bf16 — final cast of the ring accumulator ([n] fp32 -> bf16). */
+/* fa_cast_f32 — final cast of the ring accumulator: [n] fp32 -> dtype (FA_BF16 or FA_F16).  fa_cast_f32_to_bf16 is the
+ * bf16 case under its original name. */
+int fa_cast_f32(const float* src, void* dst, int64_t n, int32_t dtype, void* stream);
 int fa_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 
 /*

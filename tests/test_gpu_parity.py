@@ -115,7 +115,7 @@ def test_against_reference_kernel_golden(fab, cuda_device, path):
         pytest.skip("no golden vectors committed yet")
     g = np.load(path)
     d = int(g["d"])
-    impl = 0 if d in (32, 64) else fab.FA_IMPL_SIMT   # fp32 d=128 has no tcgen05 instance yet
+    impl = 0 if d in (32, 64) else fab.FA_IMPL_SIMT   # fp32 d=128 has no tcgen05 instance
     o = _run(fab, g["q"], g["k"], g["v"], bool(g["causal"]), 1.0, impl=impl, lse=False)
     tol = TOL_TF32_UNSCALED if impl == 0 else 1e-4
     assert np.abs(o - g["o"]).max() < tol, path
@@ -193,16 +193,62 @@ def test_four_d_and_three_d_inputs_agree(fab, cuda_device):
     assert torch.equal(o4.reshape(8, 256, 64), o3)
 
 
-@pytest.mark.parametrize("d,dtype", [(40, torch.float32), (96, torch.float32), (128, torch.float32), (96, torch.bfloat16), (256, torch.bfloat16)])
+@pytest.mark.parametrize("d,dtype", [(96, torch.float32), (128, torch.float32), (256, torch.bfloat16), (160, torch.float16)])
 def test_general_head_dims_use_the_simt_kernel(fab, oracle, cuda_device, d, dtype):
     q, k, v = seeded((2, 200, d), 71), seeded((2, 200, d), 72), seeded((2, 200, d), 73)
-    if dtype == torch.bfloat16:
-        q, k, v = _bf16_round(q), _bf16_round(k), _bf16_round(v)
+    if dtype != torch.float32:
+        q, k, v = (torch.from_numpy(x).to(dtype).float().numpy() for x in (q, k, v))
     o, lse = _run(fab, q, k, v, True, 1 / math.sqrt(d), dtype=dtype)
     assert fab.last_impl() == fab.FA_IMPL_SIMT
     o_ref, lse_ref = oracle.f64(q, k, v, 1 / math.sqrt(d), True)
     assert np.abs(o - o_ref).max() < (TOL_SIMT if dtype == torch.float32 else TOL_BF16)
     assert np.abs(lse - lse_ref).max() < 1e-4
+
+
+@pytest.mark.parametrize("d,dtype", [(8, torch.float32), (40, torch.float32), (48, torch.float32), (16, torch.bfloat16), (32, torch.bfloat16),
+                                     (80, torch.bfloat16), (96, torch.bfloat16), (112, torch.float16), (24, torch.float16)])
+@pytest.mark.parametrize("causal", [False, True])
+def test_head_dims_below_an_instance_are_zero_padded_by_tma(fab, oracle, cuda_device, d, dtype, causal):
+    """Head dims that do not fill a 128- / 256-byte tile row run on the next tcgen05 instance up: TMA zero-fills the
+    missing Q/K/V columns and clips them from the O store.  n = 333 also exercises the row tails; the guard columns after
+    every O row must stay untouched (the clipped columns are really not written)."""
+    n = 333
+    q, k, v = seeded((3, n, d), 171), seeded((3, n, d), 172), seeded((3, n, d), 173)
+    if dtype != torch.float32:
+        q, k, v = (torch.from_numpy(x).to(dtype).float().numpy() for x in (q, k, v))
+    o, lse = _run(fab, q, k, v, causal, 1 / math.sqrt(d), dtype=dtype)
+    assert fab.last_impl() == fab.FA_IMPL_TCGEN05
+    o_ref, lse_ref = oracle.f64(q, k, v, 1 / math.sqrt(d), causal)
+    if dtype == torch.float32:
+        assert tf32_err(o, o_ref) < TOL_TF32_FEWKEYS
+    else:
+        assert np.abs(o - o_ref).max() < TOL_BF16
+    assert np.abs(lse - lse_ref).max() < 2e-3
+    # same problem on the CUDA-core kernel: the two GPU paths agree as well
+    o_simt = _run(fab, q, k, v, causal, 1 / math.sqrt(d), dtype=dtype, impl=fab.FA_IMPL_SIMT, lse=False) if d % 8 == 0 else None
+    if o_simt is not None:
+        assert np.abs(o - o_simt).max() < (TOL_TF32_FEWKEYS * 3 if dtype == torch.float32 else TOL_BF16)
+
+
+@pytest.mark.parametrize("d,n,causal", [(128, 1000, False), (128, 777, True), (64, 512, False), (64, 300, True)])
+def test_fp16_path_vs_oracle(fab, oracle, cuda_device, d, n, causal):
+    """IEEE fp16 operands (FA_F16): kind::f16 with operand format 0; P is at most 2^8 by the lazy-rescale rule, far inside
+    the fp16 range, and carries 3 more mantissa bits than bf16 — the tolerance is the bf16 one, the measured error lower."""
+    q, k, v = (torch.from_numpy(seeded((4, n, d), 181 + i)).to(torch.float16).float().numpy() for i in range(3))
+    o, lse = _run(fab, q, k, v, causal, 1 / math.sqrt(d), dtype=torch.float16)
+    assert fab.last_impl() == fab.FA_IMPL_TCGEN05
+    o_ref, lse_ref = oracle.f64(q, k, v, 1 / math.sqrt(d), causal)
+    err = np.abs(o - o_ref).max()
+    assert err < TOL_BF16 / 4, err
+    assert np.abs(lse - lse_ref).max() < 1e-3
+    # fp32 output of the same instance family (what the ring merge consumes) and the final cast back to fp16
+    dev = torch.device("cuda:0")
+    tq, tk, tv = (torch.from_numpy(x).to(dev).to(torch.float16) for x in (q, k, v))
+    o32 = fab.attention(tq, tk, tv, causal=causal, out_f32=True)
+    assert o32.dtype == torch.float32 and np.abs(o32.cpu().numpy() - o_ref).max() < TOL_BF16 / 4
+    from flashattention_c_b200 import api
+    o16 = api.cast_to_16(o32, torch.float16)
+    assert o16.dtype == torch.float16 and torch.equal(o16, o32.to(torch.float16))
 
 
 def test_simt_checker_matches_oracle_tightly(fab, oracle, cuda_device):
