@@ -220,14 +220,19 @@ int launch_tc_c(bool causal, const CUtensorMap& mq, const CUtensorMap& mk, const
                 : launch_tc<kTF32, kHeadDim, false, kOutF32, kF16>(mq, mk, mv, mo, fp, st);
 }
 
-// The tcgen05 kernel is instantiated for tile rows of 128 and 256 bytes: fp32 head dims 32 / 64, 16-bit head dims 64 / 128.
-// Any smaller head dim whose rows keep TMA's 16-byte alignment runs on the next instance up: TMA zero-fills the missing
-// columns of Q, K and V in SMEM (zero columns add nothing to q.k, and give zero O columns) and clips them from the O store.
-// 0 = no instance (fp32 d > 64, 16-bit d > 128: CUDA-core kernel).
+// The tcgen05 kernel is instantiated for tile rows of 128, 256 and 512 bytes: fp32 head dims 32 / 64 / 128, 16-bit head
+// dims 64 / 128 / 256 (the 512-byte instances keep one Q tile per CTA: FwdTraits::kSlots).  Any smaller head dim whose
+// rows keep TMA's 16-byte alignment runs on the next instance up: TMA zero-fills the missing columns of Q, K and V in SMEM
+// (zero columns add nothing to q.k, and give zero O columns) and clips them from the O store.
+// 0 = no instance (fp32 d > 128: CUDA-core kernel; FA_B200_NO_WIDE=1 also sends the 512-byte rows there, A/B aid).
 int tc_instance_dim(const fa_params* p) {
   const int d = p->head_dim;
-  if (p->dtype == FA_F32) return (d % 4 || d > 64) ? 0 : (d <= 32 ? 32 : 64);
-  return (d % 8 || d > 128) ? 0 : (d <= 64 ? 64 : 128);
+  static const bool no_wide = [] { const char* e = getenv("FA_B200_NO_WIDE"); return e && atoi(e) != 0; }();
+  int di;
+  if (p->dtype == FA_F32) di = (d % 4 || d > 128) ? 0 : (d <= 32 ? 32 : (d <= 64 ? 64 : 128));
+  else di = (d % 8 || d > 256) ? 0 : (d <= 64 ? 64 : (d <= 128 ? 128 : 256));
+  if (no_wide && di * (p->dtype == FA_F32 ? 4 : 2) > 256) di = 0;
+  return di;
 }
 bool tc_supported(const fa_params* p) { return tc_instance_dim(p) != 0; }
 
@@ -269,11 +274,13 @@ int run_tc(const fa_params* p, cudaStream_t st) {
     const int64_t sms = std::max(1, current_sm_count());
     int64_t n_big = (nb / sms) * sms;
     if (2 * (nb - n_big) > sms || getenv("FA_B200_NO_SPLIT_WAVE")) n_big = nb;
+    const bool one_slot = tc_instance_dim(p) * in_sz > 256;   // 512-byte rows: one Q tile per CTA, every item is a 128-row item
+    if (one_slot) n_big = 0;
     if (n_big > 0x3fffffff) return FA_ERR_INVALID_ARG;
     fp.n_big = (int)n_big;
     // the remainder CTAs split their K/V range over the two tile slots (FA_B200_TAIL_SPLIT=0: one slot, A/B aid)
     const char* ts = getenv("FA_B200_TAIL_SPLIT");   // read per call so a test can compare both modes in one process
-    fp.tail_split = ((ts && atoi(ts) == 0) || (p->flags & FA_FLAG_BATCH_INVARIANT)) ? 0 : 1;
+    fp.tail_split = ((ts && atoi(ts) == 0) || (p->flags & FA_FLAG_BATCH_INVARIANT) || one_slot) ? 0 : 1;
     const int64_t n_items = n_big + 2 * (nb - n_big);
     if (n_items > 0x7fffffff) return FA_ERR_INVALID_ARG;
     fp.n_items = (int)n_items;
@@ -318,12 +325,15 @@ int run_tc(const fa_params* p, cudaStream_t st) {
   if (!bf16) {
     if (di == 32) return launch_tc_c<true, 32, false>(c, mq, mk, mv, mo, fp, st);
     if (di == 64) return launch_tc_c<true, 64, false>(c, mq, mk, mv, mo, fp, st);
+    if (di == 128) return launch_tc_c<true, 128, false>(c, mq, mk, mv, mo, fp, st);
   } else if (!p->o_f32) {
     if (di == 64) return f16 ? launch_tc_c<false, 64, false, true>(c, mq, mk, mv, mo, fp, st) : launch_tc_c<false, 64, false>(c, mq, mk, mv, mo, fp, st);
     if (di == 128) return f16 ? launch_tc_c<false, 128, false, true>(c, mq, mk, mv, mo, fp, st) : launch_tc_c<false, 128, false>(c, mq, mk, mv, mo, fp, st);
+    if (di == 256) return f16 ? launch_tc_c<false, 256, false, true>(c, mq, mk, mv, mo, fp, st) : launch_tc_c<false, 256, false>(c, mq, mk, mv, mo, fp, st);
   } else {
     if (di == 64) return f16 ? launch_tc_c<false, 64, true, true>(c, mq, mk, mv, mo, fp, st) : launch_tc_c<false, 64, true>(c, mq, mk, mv, mo, fp, st);
     if (di == 128) return f16 ? launch_tc_c<false, 128, true, true>(c, mq, mk, mv, mo, fp, st) : launch_tc_c<false, 128, true>(c, mq, mk, mv, mo, fp, st);
+    if (di == 256) return f16 ? launch_tc_c<false, 256, true, true>(c, mq, mk, mv, mo, fp, st) : launch_tc_c<false, 256, true>(c, mq, mk, mv, mo, fp, st);
   }
   return FA_ERR_UNSUPPORTED;
 }

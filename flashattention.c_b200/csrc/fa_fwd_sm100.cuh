@@ -34,7 +34,7 @@
 // TMEM columns (512 allocated): S_A [0,128)  S_B [128,256)  O_A [256,256+d)  O_B [256+d, 256+2d).
 // P aliases S: bf16 path packs two bf16 per column into S cols [0,64); tf32 path overwrites S in place.
 //
-// SMEM (dynamic, 1024-B aligned): kQSets x (Q_A | Q_B) | ring of NBUF K/V tiles | barriers | work queue | (m, l)
+// SMEM (dynamic, 1024-B aligned): kQSets x (Q_A | Q_B) (Q_A only with 512-byte rows) | ring of NBUF K/V tiles | barriers | work queue | (m, l)
 // exchange.  Every tile is DCHUNKS boxes of [128 rows x 128 bytes] in the SWIZZLE_128B layout that TMA writes and
 // the UMMA descriptors read.  A slot's Q buffer doubles as the staging buffer of its O tile for the TMA store.
 #pragma once
@@ -144,7 +144,12 @@ struct FwdTraits {
   static constexpr int kElemsPerChunk = 128 / kInSize;
   static constexpr int kOutElemsPerChunk = 128 / kOutSize;
   static constexpr int kTileBytes = kDChunks * kChunkBytes;
-  static constexpr int kNBuf = kDChunks == 1 ? 8 : 5;          // K/V ring depth (tiles)
+  // Tile slots with their own Q buffer.  512-byte rows (fp32 d = 128, 16-bit d = 256) leave SMEM for one Q tile and a
+  // two-tile K/V ring only: those instances run every item as a 128-row item on slot A (the host never builds 256-row
+  // or split-KV items for them) and slot B's warps idle.  K_(j+1) then streams in under the softmax of step j and
+  // V_(j+1) under Q K^T(j+1) and that softmax — the tensor pipe has nothing else to do for a lone Q tile anyway.
+  static constexpr int kSlots = kDChunks <= 2 ? 2 : 1;
+  static constexpr int kNBuf = kDChunks == 1 ? 8 : (kDChunks == 2 ? 5 : 2);   // K/V ring depth (tiles)
   static constexpr int kUmmaK = 32 / kInSize;                  // K per tcgen05.mma: 8 (tf32) / 16 (bf16)
   static constexpr int kQSets = kDChunks == 1 ? 2 : 1;         // Q double-buffered across items where SMEM allows
   static constexpr bool kComp = kTF32 && (FA_OPT_TF32_COMP != 0);   // tf32 truncation compensated instead of reproduced
@@ -153,7 +158,7 @@ struct FwdTraits {
   static_assert(kSplitKeys == 64 || kSplitKeys == 96, "P split point");
   static constexpr int kPolyNum = kTF32 ? FA_POLY_NUM_TF32 : FA_POLY_NUM_BF16;   // polynomial exp2 on kPolyNum of every
   static constexpr int kPolyDen = kTF32 ? FA_POLY_DEN_TF32 : FA_POLY_DEN_BF16;   // kPolyDen element pairs (packed path only)
-  static constexpr int kSmemData = (2 * kQSets + kNBuf) * kTileBytes;
+  static constexpr int kSmemData = (kSlots * kQSets + kNBuf) * kTileBytes;
   static constexpr int kNumBarriers = 4 * kQSets /*q full, q free*/ + 2 * kNBuf + 2 /*s_full*/ + 4 /*p_full halves*/ +
                                       2 /*o_final*/ + 2 /*o_free*/ + 2 * kWorkQueue + 2 /*pv1 done*/;
   static constexpr int kSmemBytes = kSmemData + kNumBarriers * 8 + 16 /*tmem ptr*/ + kWorkQueue * 4 + 2 * kBlockM * 4 /*m, l*/ +
@@ -163,8 +168,11 @@ struct FwdTraits {
   static constexpr int kP1Cols = (kBlockN - kSplitKeys) * kInSize / 4;   // TMEM columns of the second piece of P
   static constexpr int kTmemP1 = 256 + 2 * kHeadDim;                      // + kP1Cols*t (kEarlyS only)
   static constexpr bool kEarlyS = (FA_OPT_EARLY_S != 0) && (FA_OPT_SPLITP != 0) && (256 + 2 * kHeadDim + 2 * kP1Cols <= 512);
-  static_assert(kDChunks == 1 || kDChunks == 2, "tile row must be 128 or 256 bytes");
-  static_assert(256 + 2 * kHeadDim <= 512, "TMEM budget");
+  static_assert(kDChunks == 1 || kDChunks == 2 || kDChunks == 4, "tile row must be 128, 256 or 512 bytes");
+  static_assert(256 + kSlots * kHeadDim <= 512, "TMEM budget");
+  static_assert(kSmemBytes <= 227 * 1024, "SMEM budget");
+  // SMEM tile index of Q buffer qb = set * 2 + slot (the barrier index): one-slot instances have no tile for slot B
+  __host__ __device__ static constexpr int q_tile(int qb) { return kSlots == 2 ? qb : (qb >> 1); }
 };
 
 // watchdog tags
@@ -235,8 +243,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   constexpr int kQS = T::kQSets;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base;                              // [kQS][2] tiles
-  const uint32_t sKV = smem_base + 2 * kQS * T::kTileBytes;   // kNBuf tiles
+  const uint32_t sQ = smem_base;                              // [kQS][kSlots] tiles
+  const uint32_t sKV = smem_base + T::kSlots * kQS * T::kTileBytes;   // kNBuf tiles
   const uint32_t sBar = smem_base + T::kSmemData;
   const uint32_t bar_q = sBar;                                // [kQS][2]  Q tile landed
   const uint32_t bar_qfree = bar_q + 16 * kQS;                // [kQS][2]  Q buffer (= O staging) reusable
@@ -361,7 +369,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               mbar_arrive_expect_tx(bar_q + 8 * qb, T::kTileBytes);
 #pragma unroll
               for (int c = 0; c < T::kDChunks; ++c)
-                tma_load_4d(sQ + qb * T::kTileBytes + c * kChunkBytes, &tm_q, bar_q + 8 * qb, c * T::kElemsPerChunk,
+                tma_load_4d(sQ + T::q_tile(qb) * T::kTileBytes + c * kChunkBytes, &tm_q, bar_q + 8 * qb, c * T::kElemsPerChunk,
                             w.row0 + t * kBlockM, w.head, w.batch);
             }
           }
@@ -425,7 +433,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     // Descriptors are built once per operand tile; a k-step only adds to the 14-bit start-address field
     // ((bytes >> 4); SMEM addresses are < 2^18, so the field never carries).
     auto issue_s = [&](int t, int qbuf, int buf) {
-      const uint64_t qd = sdesc_at(hi_kmajor, sQ + qbuf * T::kTileBytes);
+      const uint64_t qd = sdesc_at(hi_kmajor, sQ + T::q_tile(qbuf) * T::kTileBytes);
       const uint64_t kd = sdesc_at(hi_kmajor, sKV + buf * T::kTileBytes);
       const uint32_t d = tmem_base + T::kTmemS + t * kBlockN;
 #pragma unroll
@@ -872,7 +880,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           lse_val = l_all > 0.f ? m_all * p.scale + logf(l_all) : -INFINITY;
         }
       }
-      const uint32_t stage = sQ + (set * 2 + t) * T::kTileBytes;   // kDChunks boxes of 16 KB
+      const uint32_t stage = sQ + T::q_tile(set * 2 + t) * T::kTileBytes;   // kDChunks boxes of 16 KB (slot B of a one-slot
+                                                                            // instance never stores: `stores` below)
       const uint32_t row_off = r * 128;
       const uint32_t sw = r & 7;
       constexpr int kRounds = T::kOChunks / T::kDChunks;   // 1, or 2 for bf16-in / fp32-out

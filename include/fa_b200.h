@@ -61,9 +61,9 @@ typedef struct fa_params {
   void* o;                 /* same dtype as q unless o_f32 != 0 */
   float* lse;              /* optional [batch, heads, n_q] contiguous fp32; may be NULL */
   int64_t batch, heads, n_q, n_k;
-  int32_t head_dim;        /* tcgen05 path: fp32 d <= 64 (d % 4 == 0), bf16 / fp16 d <= 128 (d % 8 == 0) — kernel instances exist
-                              for 128- and 256-byte rows, smaller head dims are zero-padded by TMA; larger ones up to 256
-                              (d % 8 == 0) run on the CUDA-core kernel */
+  int32_t head_dim;        /* tcgen05 path: fp32 d <= 128 (d % 4 == 0), bf16 / fp16 d <= 256 (d % 8 == 0) — kernel instances exist
+                              for 128-, 256- and 512-byte rows, head dims in between are zero-padded by TMA; fp32 d up to
+                              256 (d % 8 == 0) runs on the CUDA-core kernel */
   int32_t dtype;           /* enum fa_dtype */
   int32_t causal;          /* 0 / 1.  Causal is bottom-right aligned: key j visible to row i iff j <= i + (n_k - n_q) */
   int32_t o_f32;           /* bf16 / fp16 inputs only: write O as fp32 (used by the ring merge) */
