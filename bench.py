@@ -155,6 +155,33 @@ def cpu_baseline(torch, N, d, budget_s=12.0):
                       f"{dt:.1f} s, scaled linearly"}
 
 
+def reference_cpu_loop(budget_s=10.0):
+    """The reference's own CPU implementation of the path — attention_forward_cpu (src/llm.c/attention_forward.cu:53-125:
+    causal, 1/sqrt(hs), scalar single-threaded C) — from oracle/_ref/libllmc_ref.so, timed on a bounded sample.
+    None where the reference was not compiled (oracle/_ref absent)."""
+    import numpy as np
+
+    from oracle import fa_oracle
+
+    B, T, NH, hs = 1, 1024, 4, 64
+    C = NH * hs
+    inp = np.random.default_rng(0).random((B, T, 3 * C), dtype=np.float32) * 2 - 1
+    if fa_oracle.ref_llmc_cpu(inp, B, T, C, NH) is None:   # warm-up + availability
+        return None
+    t0 = time.perf_counter()
+    n = 0
+    while n < 20:
+        fa_oracle.ref_llmc_cpu(inp, B, T, C, NH)
+        n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = (time.perf_counter() - t0) / n
+    fl = 4.0 * B * NH * hs * T * (T + 1) / 2   # visible (query, key) pairs x 2 contractions x 2 FLOP
+    return {"value": round(fl / dt * 1e-12, 6), "unit": "TFLOP/s", "cores": 1, "kind": "reference",
+            "sample": f"reference attention_forward_cpu (llm.c CPU loop, causal, scalar, 1 thread): B={B} T={T} NH={NH} hs={hs}, "
+                      f"{n} calls of {dt * 1e3:.1f} ms; FLOPs counted over the visible pairs only"}
+
+
 def run_ours(args, torch, dist, rank, world, device):
     import flashattention_c_b200 as fab
 
@@ -233,6 +260,7 @@ def run_ours(args, torch, dist, rank, world, device):
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(torch, N, d)
+        line["cpu_baseline"]["reference_cpu_loop"] = reference_cpu_loop(5.0)   # the reference's own scalar CPU loop, beside it
     if world == 1 and not args.no_extra:
         line["other_configs"] = other_configs(torch, fab, device, flush, peaks)
     return line
@@ -295,8 +323,11 @@ def run_reference(args, torch, rank, world, device):
                                                             "flash_tiled_coarse rebuilt for sm_100a (oracle/_ref), its forward() incl. torch::zeros + cudaDeviceSynchronize, scale fixed at 1.0"},
                      "e2e": {"value": round(fl / e2e_s * 1e-12, 3), "unit": "TFLOP/s", "ms_per_step": round(e2e_s * 1e3, 3),
                              "h2d_bytes_per_step": 3 * q.numel() * 4, "d2h_bytes_per_step": q.numel() * 4},
-                     "cpu_baseline": {"value": None, "unit": "TFLOP/s", "cores": 0, "kind": "reference",
-                                      "sample": "the reference for this path is a CUDA kernel; it ran on the GPU, not on host cores"}})
+                     "cpu_baseline": reference_cpu_loop() or {
+                         "value": None, "unit": "TFLOP/s", "cores": 0, "kind": "reference",
+                         "sample": "the reference for this path is a CUDA kernel; it ran on the GPU, not on host cores"}})
+        base["cpu_baseline"]["note"] = ("the reference's implementation of this path is a CUDA kernel: `value` and `e2e` of this line are "
+                                        "that kernel on the same GPU; cpu_baseline is the only CPU code the reference has for it")
         return base
     # no reference build on this box: time the oracle's CPU port of the same algorithm on a bounded sample
     import numpy as np
