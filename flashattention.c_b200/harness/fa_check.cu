@@ -3,7 +3,7 @@
 // For each run it (1) launches the tcgen05 path and the SIMT path on the same seeded N(0,1) inputs and
 // reports their max-abs difference over the whole tensor, (2) checks sampled rows of both against an fp64
 // host evaluation of softmax(scale*q.K^T [+causal]) V, (3) times the tcgen05 path with CUDA events
-// (L2 flushed between repetitions) and prints one JSON line.
+// (L2 flushed between repetitions; FA_CHECK_TIME_IMPL=2 times the CUDA-core kernel instead) and prints one JSON line.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -171,6 +171,7 @@ int main(int argc, char** argv) {
 
   // timing (tcgen05 path), L2 flushed between repetitions
   p.o = do_tc; p.lse = nullptr; p.impl = FA_IMPL_TCGEN05;
+  if (const char* ti = getenv("FA_CHECK_TIME_IMPL")) p.impl = atoi(ti);   // 2 = time the CUDA-core kernel instead
   void* flush;
   const size_t flush_bytes = 256u << 20;
   CK(cudaMalloc(&flush, flush_bytes));
