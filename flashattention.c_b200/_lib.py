@@ -18,6 +18,7 @@ EXPORTED_SYMBOLS = [
     "run_flash_tiled_coarse", "run_flash_tiled_coarse_causal", "attention_forward6", "attention_forward",
     "fa_strerror", "fa_last_cuda_error", "fa_last_impl", "fa_version", "fa_launch_count",
     "fa_watchdog_info",
+    "fa_p2p_alloc", "fa_p2p_open", "fa_p2p_close", "fa_p2p_free", "fa_copy_async",
 ]
 
 
@@ -66,6 +67,16 @@ def lib() -> ctypes.CDLL:
         L.fa_cast_f32.restype = ctypes.c_int
         L.fa_cast_f32_to_bf16.argtypes = [vp, vp, i64, vp]
         L.fa_cast_f32_to_bf16.restype = ctypes.c_int
+        L.fa_p2p_alloc.argtypes = [i64, ctypes.POINTER(vp), ctypes.c_char_p]
+        L.fa_p2p_alloc.restype = ctypes.c_int
+        L.fa_p2p_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+        L.fa_p2p_open.restype = ctypes.c_int
+        L.fa_p2p_close.argtypes = [vp]
+        L.fa_p2p_close.restype = ctypes.c_int
+        L.fa_p2p_free.argtypes = [vp]
+        L.fa_p2p_free.restype = ctypes.c_int
+        L.fa_copy_async.argtypes = [vp, vp, i64, vp]
+        L.fa_copy_async.restype = ctypes.c_int
         L.fa_strerror.argtypes = [ctypes.c_int]
         L.fa_strerror.restype = ctypes.c_char_p
         L.fa_last_cuda_error.argtypes = []

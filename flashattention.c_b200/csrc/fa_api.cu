@@ -599,6 +599,54 @@ int fa_cast_f32(const float* src, void* dst, int64_t n, int32_t dtype, void* str
 }
 int fa_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) { return fa_cast_f32(src, dst, n, FA_BF16, stream); }
 
+// ------------------------------ peer-to-peer staging (ring forward) ------------------------------
+// One process per GPU: a rank exports its K/V shard buffer as a CUDA IPC handle, every other rank maps it and pulls the
+// shard it needs next with a plain device-to-device cudaMemcpyAsync — a copy-engine transfer over NVLink that needs no SM,
+// so it runs under the persistent attention kernel (which owns every SM for the whole step).
+int fa_p2p_alloc(int64_t bytes, void** ptr, uint8_t handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  if (bytes <= 0 || !ptr || !handle) return FA_ERR_INVALID_ARG;
+  int major = 0;
+  int rc = probe_device(&major);
+  if (rc) return rc;
+  void* p = nullptr;
+  FA_CUDA(cudaMalloc(&p, (size_t)bytes));   // its own allocation: the IPC handle then maps exactly this buffer at offset 0
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return cuda_fail(e, "cudaIpcGetMemHandle");
+  }
+  memcpy(handle, &h, 64);
+  *ptr = p;
+  return FA_OK;
+}
+int fa_p2p_open(const uint8_t handle[64], void** peer_ptr) {
+  if (!handle || !peer_ptr) return FA_ERR_INVALID_ARG;
+  int major = 0;
+  int rc = probe_device(&major);
+  if (rc) return rc;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  FA_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return FA_OK;
+}
+int fa_p2p_close(void* peer_ptr) {
+  if (!peer_ptr) return FA_ERR_INVALID_ARG;
+  FA_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+  return FA_OK;
+}
+int fa_p2p_free(void* ptr) {
+  if (!ptr) return FA_ERR_INVALID_ARG;
+  FA_CUDA(cudaFree(ptr));
+  return FA_OK;
+}
+int fa_copy_async(void* dst, const void* src, int64_t bytes, void* stream) {
+  if (!dst || !src || bytes <= 0) return FA_ERR_INVALID_ARG;
+  FA_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return FA_OK;
+}
+
 // ------------------------------ reference-named shims ------------------------------
 static void die_on(int rc, const char* where) {
   if (rc != FA_OK) {

@@ -7,9 +7,16 @@ Neither exists in the reference (single GPU only) — their oracl
       forward.  NO collective is on the data path; `gather_bh` exists only for parity checks.
 
   Ring attention (config 5): Q, K, V are partitioned along the sequence.  In step s rank r attends its Q shard to
-      the K/V shard that started on rank (r - s) mod P while the next shard moves r -> r+1 with NCCL send/recv
-      on a side stream (double-buffered, overlapped with the tile loop of the local kernel); partial (O, LSE)
-      pairs are merged with the log-sum-exp rule by fa_merge_partials.
+      the K/V shard that started on rank (r - s) mod P while the next shard is on its way into a ping-pong staging
+      buffer; partial (O, LSE) pairs are merged with the log-sum-exp rule by fa_merge_partials.  Two transports:
+        "p2p"  (default on GPUs) every rank publishes its K/V shard in a CUDA-IPC-exported buffer and PULLS the shard
+               it needs next straight from its owner with a device-to-device copy (fa_copy_async): a copy-engine
+               transfer over NVLink / NVSwitch that needs no SM, so it really runs under the persistent attention
+               kernel, which owns all 148 SMs for the whole step.  The shards never change, so there is no
+               rotation chain: one barrier after publishing, one before the buffers may be reused.
+        "nccl" K/V rotate r -> r+1 with NCCL send/recv on a side stream.  An NCCL kernel needs SMs; launched next
+               to a persistent kernel it runs before or after it, not under it: measured, ring time = compute +
+               transfer (profiles/r01_ring_nccl_settings_2gpu.log).  Kept for comparison and for the CPU (gloo) tests.
 
   Causal ring, balanced (zig-zag): with contiguous sequence shards a causal ring is lopsided — rank 0 has one shard
       of visible keys, rank P-1 has P.  `zigzag=True` cuts the sequence into 2P chunks and gives rank r chunks r and
@@ -101,10 +108,120 @@ def ring_schedule(rank: int, world: int):
     return [(s, (rank - s) % world) for s in range(world)]
 
 
-def ring_attention(q, k, v, causal=False, scale=None, group=None, zigzag=False, _attn=None, _merge=None, _finalize=None):
+class _P2PState:
+    """This rank's exported K/V buffer, the mappings of every peer's, the staging ping-pong and the side stream — cached per
+    (process group, shard bytes, device) and reused by every call."""
+
+    def __init__(self, nbytes, like, group):
+        import ctypes
+
+        from ._lib import check, lib
+
+        self.L, self.check = lib(), check
+        self.group, self.nbytes, self.dev = group, nbytes, like.device
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        check(self.L.fa_p2p_alloc(nbytes, ctypes.byref(ptr), handle), "fa_p2p_alloc")
+        self.local = ptr.value
+        mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=self.dev)
+        handles = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(handles, mine, group=group)
+        self.peer = []
+        for r in range(world):
+            if r == rank:
+                self.peer.append(self.local)
+            else:
+                pp = ctypes.c_void_p()
+                check(self.L.fa_p2p_open(bytes(handles[r].cpu().tolist()), ctypes.byref(pp)), f"fa_p2p_open (rank {r})")
+                self.peer.append(pp.value)
+        self.side = torch.cuda.Stream(device=self.dev)
+        self.flag = torch.zeros(1, device=self.dev)
+        # staging ping-pong [2][K | V], shaped like the caller's shards
+        self.stage = [torch.empty((2,) + tuple(like.shape), dtype=like.dtype, device=self.dev) for _ in range(2)]
+
+    def copy(self, dst_ptr, src_ptr, nbytes, stream):
+        import ctypes
+
+        self.check(self.L.fa_copy_async(ctypes.c_void_p(dst_ptr), ctypes.c_void_p(src_ptr), nbytes, ctypes.c_void_p(stream.cuda_stream)),
+                   "fa_copy_async")
+
+    def barrier(self):
+        """Stream-ordered barrier on the current stream: completes on a rank only when every rank's stream has reached it."""
+        dist.all_reduce(self.flag, group=self.group)
+
+
+_p2p_states = {}
+
+
+def _p2p_state(k, group):
+    key = (id(group) if group is not None else 0, k.device.index, tuple(k.shape), k.dtype)
+    st = _p2p_states.get(key)
+    if st is None:
+        st = _p2p_states[key] = _P2PState(2 * k.numel() * k.element_size(), k, group)
+    return st
+
+
+def _ring_p2p(q, k, v, causal, zz, c, attn, merge, group, rank, world):
+    """The ring forward over the p2p transport (see the module docstring).  Returns the fp32 accumulator and the LSE."""
+    st = _p2p_state(k, group)
+    main = torch.cuda.current_stream(q.device)
+    kc, vc = k.contiguous(), v.contiguous()
+    half = st.nbytes // 2
+    # publish this rank's shard, then wait until every rank has published
+    st.copy(st.local, kc.data_ptr(), half, main)
+    st.copy(st.local + half, vc.data_ptr(), half, main)
+    st.barrier()
+    ev_start = torch.cuda.Event()
+    ev_start.record(main)
+    # the remote shards this rank needs, in ring order (a causal ring with contiguous shards never looks at later ranks)
+    remote = [src for _, src in ring_schedule(rank, world)[1:] if zz or not causal or src < rank]
+    ev_copy, ev_free = [None] * len(remote), [None, None]
+
+    def prefetch(i):
+        with torch.cuda.stream(st.side):
+            st.side.wait_event(ev_start)
+            if ev_free[i % 2] is not None:
+                st.side.wait_event(ev_free[i % 2])    # the kernels that read this staging buffer two steps ago are done
+            st.copy(st.stage[i % 2].data_ptr(), st.peer[remote[i]], st.nbytes, st.side)
+            ev_copy[i] = torch.cuda.Event()
+            ev_copy[i].record(st.side)
+
+    acc = [[None, None], [None, None]]   # zig-zag: one accumulator per query chunk; otherwise acc[0]
+
+    def accumulate(slot, o_s, lse_s):
+        acc[slot] = [o_s, lse_s] if acc[slot][0] is None else list(merge(acc[slot][0], acc[slot][1], o_s, lse_s))
+
+    def compute(src, k_s, v_s):
+        if zz:
+            for hq, keys, cz in zigzag_step_plan(rank, src):
+                kk, vv = (k_s, v_s) if keys == "all" else (k_s[..., :c, :], v_s[..., :c, :])
+                accumulate(hq, *attn(q[..., hq * c:(hq + 1) * c, :], kk, vv, cz))
+        else:
+            accumulate(0, *attn(q, k_s, v_s, bool(causal and src == rank)))
+
+    if remote:
+        prefetch(0)
+    compute(rank, kc, vc)                      # the local shard, while the first remote shard is on its way
+    for i, src in enumerate(remote):
+        if i + 1 < len(remote):
+            prefetch(i + 1)
+        main.wait_event(ev_copy[i])
+        compute(src, st.stage[i % 2][0], st.stage[i % 2][1])
+        ev_free[i % 2] = torch.cuda.Event()
+        ev_free[i % 2].record(main)
+    st.barrier()                               # nobody is still pulling from a buffer the next call will overwrite
+    if zz:
+        return torch.cat([acc[0][0], acc[1][0]], dim=-2), torch.cat([acc[0][1], acc[1][1]], dim=-1)
+    return acc[0][0], acc[0][1]
+
+
+def ring_attention(q, k, v, causal=False, scale=None, group=None, zigzag=False, transport=None, _attn=None, _merge=None,
+                   _finalize=None):
     """Sequence-partitioned forward.  q, k, v: this rank's shards [B, H, N/P, d] (or [B*H, N/P, d]), rank r holding
     sequence positions [r*N/P, (r+1)*N/P) — or, with zigzag=True (causal only), chunks r and 2P-1-r of 2P
     (zigzag_shard).  Returns this rank's shard of O in q's dtype and the fp32 LSE, in the same layout as q.
+    transport: "p2p" (copy-engine pulls from CUDA-IPC-mapped peer buffers; the default for CUDA tensors) or "nccl"
+    (send/recv rotation; the default for the CPU test seams).
 
     `_attn`, `_merge`, `_finalize` are test seams (the gloo/CPU tests inject the oracle to exercise the rotation and the
     merge without a GPU); the product path leaves them None and runs the CUDA kernels.
@@ -137,6 +254,17 @@ def ring_attention(q, k, v, causal=False, scale=None, group=None, zigzag=False, 
     if world == 1:
         o, lse = attn(q, k, v, causal)
         return (_finalize(o) if _finalize else (api.cast_to_16(o, q.dtype) if (on_gpu and q.dtype != torch.float32) else o)), lse
+    if transport is None:
+        transport = "p2p" if (on_gpu and _attn is None) else "nccl"
+    if transport not in ("p2p", "nccl"):
+        raise ValueError(f"unknown ring transport {transport!r}")
+    if transport == "p2p":
+        if not on_gpu:
+            raise ValueError("the p2p transport needs CUDA tensors")
+        o_acc, lse_acc = _ring_p2p(q, k, v, causal, zz, c, attn, merge, group, rank, world)
+        if _finalize is not None:
+            return _finalize(o_acc), lse_acc
+        return (api.cast_to_16(o_acc, q.dtype) if q.dtype != torch.float32 else o_acc), lse_acc
 
     nxt = dist.get_global_rank(group, (rank + 1) % world) if group is not None else (rank + 1) % world
     prv = dist.get_global_rank(group, (rank - 1) % world) if group is not None else (rank - 1) % world

@@ -126,6 +126,20 @@ int fa_cast_f32(const float* src, void* dst, int64_t n, int32_t dtype, void* str
 int fa_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 
 /*
+ * Peer-to-peer staging for the sequence-partitioned (ring) forward, one process per GPU (not in the reference, which is
+ * single-GPU).  fa_p2p_alloc makes a device buffer and its 64-byte CUDA IPC handle; the other ranks fa_p2p_open the handle
+ * (exchanged by the host plumbing, e.g. torch.distributed all_gather) and pull the K/V shard they need next with
+ * fa_copy_async: a device-to-device copy that the copy engines run over NVLink without occupying an SM, so it overlaps the
+ * persistent attention kernel of the current step.  The caller orders the accesses (a barrier after the owners filled
+ * their buffers and one before they are reused).
+ */
+int fa_p2p_alloc(int64_t bytes, void** ptr, uint8_t handle[64]);
+int fa_p2p_open(const uint8_t handle[64], void** peer_ptr);   /* in a process other than the exporter's */
+int fa_p2p_close(void* peer_ptr);
+int fa_p2p_free(void* ptr);
+int fa_copy_async(void* dst, const void* src, int64_t bytes, void* stream);   /* src or dst may be a peer mapping */
+
+/*
  * Reference-named shims (same argument order and meaning as the reference symbols).
  *
  * run_flash_tiled_coarse / _causal: test.cu:591-603 (torch-less launchers; note the O, K, Q, V order),

@@ -6,9 +6,10 @@
 
   1. B x H sharding (configs 3/4): every rank runs its slice with no collective; the all-gathered result must equal the
      unsharded single-GPU forward bit for bit.
-  2. Ring attention (config 5): sequence shards, NCCL send/recv K/V rotation overlapped with the local kernel, LSE merge;
-     checked against the single-GPU forward over the full sequence, non-causal and causal.
-  3. Timing of the C5-shaped ring (H=32, d=128, bf16, N = n_per_rank * P): max over ranks, CUDA events.
+  2. Ring attention (config 5): sequence shards, the next K/V shard pulled from its owner by the copy engines over NVLink
+     (transport "p2p") or rotated with NCCL send/recv (transport "nccl") while the local kernel runs, LSE merge;
+     checked against the single-GPU forward over the full sequence, non-causal and causal, both transports.
+  3. Timing of the C5-shaped ring (H=32, d=128, bf16, N = n_per_rank * P), both transports: max over ranks, CUDA events.
 Prints one JSON line per item on rank 0.
 """
 import argparse
@@ -56,21 +57,24 @@ def main():
                 "local_bh": int(o_loc.shape[0])})
 
     # ---- 2. ring parity ----
-    for dtype, dd, tol in ((torch.bfloat16, 128, 2e-2), (torch.float32, 64, 2e-3)):
-        for causal in (False, True):
-            Hh, n_loc = 4, 1024
-            Nf = n_loc * world
-            gq = torch.Generator(device="cpu").manual_seed(11)
-            qf, kf, vf = (torch.randn(1, Hh, Nf, dd, generator=gq).to(dtype).to(dev) for _ in range(3))
-            sl = slice(rank * n_loc, (rank + 1) * n_loc)
-            o_r, lse_r = fab.ring_attention(qf[:, :, sl].contiguous(), kf[:, :, sl].contiguous(), vf[:, :, sl].contiguous(), causal=causal)
-            o_full, lse_full = fab.attention(qf, kf, vf, causal=causal, return_lse=True)
-            err = (o_r.float() - o_full[:, :, sl].float()).abs().max()
-            err_l = (lse_r - lse_full[:, :, sl]).abs().max()
-            t = torch.stack([err, err_l])
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            out.append({"check": f"ring_vs_single_gpu dtype={str(dtype).split('.')[-1]} d={dd} causal={causal} N={Nf}", "world": world,
-                        "max_err_o": float(t[0]), "max_err_lse": float(t[1]), "ok": bool(t[0] < tol and t[1] < 2e-3)})
+    for transport in ("p2p", "nccl"):
+        for dtype, dd, tol in ((torch.bfloat16, 128, 2e-2), (torch.float32, 64, 2e-3)):
+            for causal in (False, True):
+                Hh, n_loc = 4, 1024
+                Nf = n_loc * world
+                gq = torch.Generator(device="cpu").manual_seed(11)
+                qf, kf, vf = (torch.randn(1, Hh, Nf, dd, generator=gq).to(dtype).to(dev) for _ in range(3))
+                sl = slice(rank * n_loc, (rank + 1) * n_loc)
+                for rep in range(2):   # twice: the second call reuses the published buffer and the staging ping-pong
+                    o_r, lse_r = fab.ring_attention(qf[:, :, sl].contiguous(), kf[:, :, sl].contiguous(), vf[:, :, sl].contiguous(),
+                                                    causal=causal, transport=transport)
+                o_full, lse_full = fab.attention(qf, kf, vf, causal=causal, return_lse=True)
+                err = (o_r.float() - o_full[:, :, sl].float()).abs().max()
+                err_l = (lse_r - lse_full[:, :, sl]).abs().max()
+                t = torch.stack([err, err_l])
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                out.append({"check": f"ring_vs_single_gpu transport={transport} dtype={str(dtype).split('.')[-1]} d={dd} causal={causal} N={Nf}",
+                            "world": world, "max_err_o": float(t[0]), "max_err_lse": float(t[1]), "ok": bool(t[0] < tol and t[1] < 2e-3)})
 
     # ---- 2b. balanced (zig-zag) causal ring parity: rank r holds chunks r and 2P-1-r ----
     for dtype, dd, tol in ((torch.bfloat16, 128, 2e-2), (torch.float32, 64, 2e-3)):
@@ -90,20 +94,25 @@ def main():
     Hh, dd, n_loc = args.heads, 128, args.n_per_rank
     gq = torch.Generator(device="cuda").manual_seed(100 + rank)
     qs, ks, vs = (torch.randn(1, Hh, n_loc, dd, device=dev, generator=gq).to(torch.bfloat16) for _ in range(3))
-    fab.ring_attention(qs, ks, vs)  # warm-up (NCCL channels, kernels)
-    torch.cuda.synchronize()
-    dist.barrier()
-    times = []
-    for _ in range(args.reps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dist.barrier()
-        e0.record()
-        fab.ring_attention(qs, ks, vs)
-        e1.record()
+    def ring_ms(transport):
+        fab.ring_attention(qs, ks, vs, transport=transport)  # warm-up (IPC mappings / NCCL channels, kernels)
         torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
-    t = torch.tensor([min(times)], device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        times = []
+        for _ in range(args.reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            e0.record()
+            fab.ring_attention(qs, ks, vs, transport=transport)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        tt = torch.tensor([min(times)], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tt
+
+    t = ring_ms("p2p")
+    t_nccl = ring_ms("nccl")
     # local-only time for the same FLOPs (world steps against the resident shard, no transfers) = overlap reference
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -118,6 +127,7 @@ def main():
     flops = 4.0 * Hh * n_total * n_total * dd
     out.append({"check": f"ring_timing C5-shaped H={Hh} d={dd} bf16 N={n_total} ({n_loc}/GPU)", "world": world, "ms": round(float(t[0]), 3),
                 "tflops_total": round(flops / float(t[0]) * 1e-9, 1), "tflops_per_gpu": round(flops / float(t[0]) * 1e-9 / world, 1),
+                "transport": "p2p (copy-engine pulls over NVLink)", "ms_nccl_sendrecv": round(float(t_nccl[0]), 3),
                 "ms_compute_only_same_flops": round(float(t_local[0]), 3),
                 "kv_bytes_sent_per_gpu_per_step": 2 * Hh * n_loc * dd * 2})
     # ---- 4. causal C5-shaped ring: contiguous shards (lopsided: rank P-1 works P times as long as rank 0) vs zig-zag ----
@@ -139,8 +149,9 @@ def main():
 
     t_plain = timed(lambda: fab.ring_attention(qs, ks, vs, causal=True))
     t_zz = timed(lambda: fab.ring_attention(qs, ks, vs, causal=True, zigzag=True))
+    t_zz_nccl = timed(lambda: fab.ring_attention(qs, ks, vs, causal=True, zigzag=True, transport="nccl"))
     out.append({"check": f"causal_ring_timing H={Hh} d={dd} bf16 N={n_total}", "world": world, "ms_contiguous_shards": round(t_plain, 3),
-                "ms_zigzag": round(t_zz, 3), "tflops_total_zigzag": round(flops / 2 / t_zz * 1e-9, 1),
+                "ms_zigzag": round(t_zz, 3), "ms_zigzag_nccl_sendrecv": round(t_zz_nccl, 3), "tflops_total_zigzag": round(flops / 2 / t_zz * 1e-9, 1),
                 "tflops_per_gpu_zigzag": round(flops / 2 / t_zz * 1e-9 / world, 1)})
     if rank == 0:
         for o in out:
