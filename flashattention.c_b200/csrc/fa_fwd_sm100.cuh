@@ -65,6 +65,13 @@
                           // Correct (62 GPU tests) but measured 3-7% slower (profiles/r01_ab_early_s.log): with one in-order
                           // issuer the other slot's work queues behind this slot's second-piece wait
 #endif
+#ifndef FA_OPT_LATE_QFREE
+#define FA_OPT_LATE_QFREE 1  // two-Q-set instances: wait for an item's O store (and release its staging buffer) after the first
+                             // softmax step of the next item instead of inside the epilogue
+#endif
+#ifndef FA_OPT_RELEASE_IN_STEP
+#define FA_OPT_RELEASE_IN_STEP 1  // K/V ring slots released from inside slot B's step (one elect block less per K/V step)
+#endif
 #ifndef FA_OPT_SPLIT_KEYS
 #define FA_OPT_SPLIT_KEYS 64  // (96 measured 2-3% slower: profiles/r01_ab_tf32_comp.log) P is handed to the MMA warp in two pieces: keys [0, FA_OPT_SPLIT_KEYS) and the rest (64 or 96)
 #endif
@@ -590,14 +597,19 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #if FA_TRACE
           FA_TRACE_AT(2, steps_a, 7);      // K/V of this step landed (slot 0 of the same row = step start)
 #endif
-#pragma unroll
-          for (int t = 0; t < 2; ++t)
-            if (j < w.n(t)) step(t, j, j == w.n(t) - 1, set * 2 + t, vbuf, kbuf, false);
-          if (elect_one_sync()) {
-            tc_commit(bar_empty + 8 * vbuf);
-            if (j + 1 < w.n_max) tc_commit(bar_empty + 8 * kbuf);
+          // the ring slots of this step (V_j, K_(j+1)) are free once the last MMA that reads them has completed: slot B's
+          // P V(j) and Q K^T(j+1) when slot B is the longer one (n1 == n_max: every causal and every full item) — released
+          // from inside its step, in the elect block that issues those MMAs — else in a block of their own
+          const bool rel_in_b = FA_OPT_RELEASE_IN_STEP != 0 && w.n1 == w.n_max;
+          if (j < w.n0) step(0, j, j == w.n0 - 1, set * 2, vbuf, kbuf, false);
+          if (j < w.n1) step(1, j, j == w.n1 - 1, set * 2 + 1, vbuf, kbuf, rel_in_b);
+          if (!rel_in_b) {
+            if (elect_one_sync()) {
+              tc_commit(bar_empty + 8 * vbuf);
+              if (j + 1 < w.n_max) tc_commit(bar_empty + 8 * kbuf);
+            }
+            __syncwarp();
           }
-          __syncwarp();
 #if FA_TRACE
           FA_TRACE_AT(3, steps_b - 1, 7);  // ring slots of this step released
 #endif
@@ -655,6 +667,20 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     (void)tracer;
     int steps = 0;            // K/V steps of this slot so far, over all items (parity of bar_s / bar_p)
     uint32_t o_par = 0;       // bit u: parity of the next bar_o[u] phase (one phase per item in which slot u has work)
+    // Instances with two Q sets: the thread that issued an item's O store does not wait for the store to have read the
+    // staging buffer right away (~800 cycles in which its warp, and with it the slot's next softmax step, would stall:
+    // timeline of C3, profiles/r01_trace_small_shapes.txt) — the buffer is not needed again before the item after next.
+    // It waits, and releases the buffer to the producer, after the first softmax step of the next item instead.
+    constexpr bool kLateQFree = FA_OPT_LATE_QFREE != 0 && kQS > 1;
+    const bool store_thread = (warp & 3) == 0 && lane == 0;
+    int pend_qfree = -1;      // store_thread only: Q buffer whose O store has been issued but not yet waited for
+    auto flush_qfree = [&]() {
+      if (kLateQFree && store_thread && pend_qfree >= 0) {
+        tma_store_wait_read();
+        mbar_arrive(bar_qfree + 8 * pend_qfree);
+        pend_qfree = -1;
+      }
+    };
 
     // exp2 of keys [i0, i0 + 32) of the S row held in s[], in place, with the partial row sums in l0..l3
     auto exp_chunk = [&](float* s, const int i0, const float neg_mc, float& l0, float& l1, float& l2, float& l3) {
@@ -834,7 +860,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #endif
         }
         l += (l0 + l1) + (l2 + l3);
+        if (j == 0) flush_qfree();
       }
+      flush_qfree();   // (a slot without K/V steps in this item)
       if constexpr (T::kComp) l *= kTf32CompInv;   // the sums were taken over P*(1+eps)
 
       // ---- epilogue: O/l -> swizzled SMEM (reusing this slot's Q buffer) -> TMA store; LSE -> global ----
@@ -950,9 +978,13 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               tma_store_4d(&tm_o, stage + ch * kChunkBytes, (round * T::kDChunks + ch) * kColsPerChunk, w.row0 + t * kBlockM,
                            w.head, w.batch);
             tma_store_commit();
-            tma_store_wait_read();
+            if (kLateQFree && round + 1 == kRounds) {
+              pend_qfree = set * 2 + t;
+            } else {
+              tma_store_wait_read();
+              if (round + 1 == kRounds) mbar_arrive(bar_qfree + 8 * (set * 2 + t));   // staging buffer read out: Q may land here again
+            }
             if (seq == 0) FA_TRACE_MISC(t, 5);
-            if (round + 1 == kRounds) mbar_arrive(bar_qfree + 8 * (set * 2 + t));   // staging buffer read out: Q may land here again
           }
           if (round + 1 < kRounds) named_bar_sync(1 + t, 128);
         }
@@ -961,6 +993,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           p.lse[(static_cast<int64_t>(w.batch) * p.heads + w.head) * p.n_q + q_row] = lse_val;
       }
     }
+    flush_qfree();
     if ((warp & 3) == 0 && lane == 0) {
       tma_store_wait_all();
       FA_TRACE_MISC(t, 6);
