@@ -44,6 +44,11 @@
 #ifndef FA_OPT_SPLITP
 #define FA_OPT_SPLITP 1   // deliver P to the MMA thread in two 64-key halves so P*V overlaps the second half of the exps
 #endif
+#ifndef FA_OPT_SPLITP_NARROW
+#define FA_OPT_SPLITP_NARROW 1   // 0: the 128-byte-row instances (fp32 d <= 32, 16-bit d <= 64) hand P over in one piece: their P*V is
+                                 // short, and the MMA warp — busy for the whole step at these head dims — saves a wait and an
+                                 // elect block per slot and step
+#endif
 #ifndef FA_OPT_LDPIPE
 #define FA_OPT_LDPIPE 0   // overlap the row-max pass with the remaining tcgen05.ld of the S row
 #endif
@@ -174,7 +179,8 @@ struct FwdTraits {
   static constexpr int kTmemO = 256;      // + kHeadDim*t
   static constexpr int kP1Cols = (kBlockN - kSplitKeys) * kInSize / 4;   // TMEM columns of the second piece of P
   static constexpr int kTmemP1 = 256 + 2 * kHeadDim;                      // + kP1Cols*t (kEarlyS only)
-  static constexpr bool kEarlyS = (FA_OPT_EARLY_S != 0) && (FA_OPT_SPLITP != 0) && (256 + 2 * kHeadDim + 2 * kP1Cols <= 512);
+  static constexpr bool kSplitP = (FA_OPT_SPLITP != 0) && (kDChunks > 1 || FA_OPT_SPLITP_NARROW != 0);   // P delivered in two pieces
+  static constexpr bool kEarlyS = (FA_OPT_EARLY_S != 0) && kSplitP && (256 + 2 * kHeadDim + 2 * kP1Cols <= 512);
   static_assert(kDChunks == 1 || kDChunks == 2 || kDChunks == 4, "tile row must be 128, 256 or 512 bytes");
   static_assert(256 + kSlots * kHeadDim <= 512, "TMEM budget");
   static_assert(kSmemBytes <= 227 * 1024, "SMEM budget");
@@ -518,20 +524,20 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           if (last) tc_commit(bar_o + 8 * t);
         }
       } else {
-#if FA_OPT_SPLITP
-      FA_TRACE_AT(2 + t, g, 0);
-      mbar_wait(bar_p + 16 * t, par, TAG_P_FULL);            // keys [0, 64) of P are in TMEM
-      tc_fence_after();
-      FA_TRACE_AT(2 + t, g, 1);
-      if (elect_one_sync()) issue_pv(t, vbuf, j > 0, 0, kKStepsSplit);
-      __syncwarp();
-      FA_TRACE_AT(2 + t, g, 2);
-#endif
+      if constexpr (T::kSplitP) {
+        FA_TRACE_AT(2 + t, g, 0);
+        mbar_wait(bar_p + 16 * t, par, TAG_P_FULL);            // keys [0, 64) of P are in TMEM
+        tc_fence_after();
+        FA_TRACE_AT(2 + t, g, 1);
+        if (elect_one_sync()) issue_pv(t, vbuf, j > 0, 0, kKStepsSplit);
+        __syncwarp();
+        FA_TRACE_AT(2 + t, g, 2);
+      }
       mbar_wait(bar_p + 16 * t + 8, par, TAG_P_FULL);        // keys [64, 128)
       tc_fence_after();
       FA_TRACE_AT(2 + t, g, 3);
       if (elect_one_sync()) {
-        issue_pv(t, vbuf, j > 0, FA_OPT_SPLITP ? kKStepsSplit : 0, kKStepsPV);
+        issue_pv(t, vbuf, j > 0, T::kSplitP ? kKStepsSplit : 0, kKStepsPV);
         if (release) tc_commit(bar_empty + 8 * vbuf);
         if (last) {
           tc_commit(bar_o + 8 * t);
@@ -843,21 +849,13 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               tmem_st16(own ? tP1 + (cc - kChunks0) * 16 : tS + cc * 16, pk);
             }
           }
-#if FA_OPT_SPLITP
-          if (tracer) FA_TRACE_AT(t, g, 3 + 2 * h);
-          tc_wait_st();
-          tc_fence_before();
-          mbar_arrive(bar_p + 16 * t + 8 * h);
-          if (tracer) FA_TRACE_AT(t, g, 4 + 2 * h);
-#else
-          if (h == 1) {
-            if (tracer) FA_TRACE_AT(t, g, 5);
+          if (T::kSplitP || h == 1) {   // one-piece instances arrive once, on the second barrier
+            if (tracer) FA_TRACE_AT(t, g, 3 + 2 * h);
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(bar_p + 16 * t + 8);
-            if (tracer) FA_TRACE_AT(t, g, 6);
+            mbar_arrive(bar_p + 16 * t + 8 * h);
+            if (tracer) FA_TRACE_AT(t, g, 4 + 2 * h);
           }
-#endif
         }
         l += (l0 + l1) + (l2 + l3);
         if (j == 0) flush_qfree();

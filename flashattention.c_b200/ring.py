@@ -110,18 +110,20 @@ def ring_schedule(rank: int, world: int):
 
 class _P2PState:
     """This rank's exported K/V buffer, the mappings of every peer's, the staging ping-pong and the side stream — cached per
-    (process group, shard bytes, device) and reused by every call."""
+    (process group, shard shape, device) and reused by every call.  The five methods publish / prefetch / acquire / release /
+    finish are the transport protocol `_ring_pull` drives (the gloo tests drive the same schedule through a CPU stand-in)."""
 
-    def __init__(self, nbytes, like, group):
+    def __init__(self, like, group):
         import ctypes
 
         from ._lib import check, lib
 
         self.L, self.check = lib(), check
-        self.group, self.nbytes, self.dev = group, nbytes, like.device
+        self.group, self.dev = group, like.device
+        self.half = like.numel() * like.element_size()     # bytes of K (= bytes of V)
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
-        check(self.L.fa_p2p_alloc(nbytes, ctypes.byref(ptr), handle), "fa_p2p_alloc")
+        check(self.L.fa_p2p_alloc(2 * self.half, ctypes.byref(ptr), handle), "fa_p2p_alloc")
         self.local = ptr.value
         mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=self.dev)
         handles = [torch.empty_like(mine) for _ in range(world)]
@@ -138,16 +140,49 @@ class _P2PState:
         self.flag = torch.zeros(1, device=self.dev)
         # staging ping-pong [2][K | V], shaped like the caller's shards
         self.stage = [torch.empty((2,) + tuple(like.shape), dtype=like.dtype, device=self.dev) for _ in range(2)]
+        self.ev_copy, self.ev_free, self.ev_start = {}, [None, None], None
 
-    def copy(self, dst_ptr, src_ptr, nbytes, stream):
+    def _copy(self, dst_ptr, src_ptr, nbytes, stream):
         import ctypes
 
         self.check(self.L.fa_copy_async(ctypes.c_void_p(dst_ptr), ctypes.c_void_p(src_ptr), nbytes, ctypes.c_void_p(stream.cuda_stream)),
                    "fa_copy_async")
 
-    def barrier(self):
+    def _barrier(self):
         """Stream-ordered barrier on the current stream: completes on a rank only when every rank's stream has reached it."""
         dist.all_reduce(self.flag, group=self.group)
+
+    def publish(self, kc, vc):
+        """Copy this rank's shard into its exported buffer and wait (on the stream) until every rank has done so."""
+        main = torch.cuda.current_stream(self.dev)
+        self._copy(self.local, kc.data_ptr(), self.half, main)
+        self._copy(self.local + self.half, vc.data_ptr(), self.half, main)
+        self._barrier()
+        self.ev_start = torch.cuda.Event()
+        self.ev_start.record(main)
+        self.ev_copy, self.ev_free = {}, [None, None]
+
+    def prefetch(self, i, src):
+        """Start pulling rank `src`'s shard into staging buffer i % 2 on the side stream (copy engine, no SM)."""
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev_start)
+            if self.ev_free[i % 2] is not None:
+                self.side.wait_event(self.ev_free[i % 2])    # the kernels that read this buffer two steps ago are done
+            self._copy(self.stage[i % 2].data_ptr(), self.peer[src], 2 * self.half, self.side)
+            self.ev_copy[i] = torch.cuda.Event()
+            self.ev_copy[i].record(self.side)
+
+    def acquire(self, i, src):
+        """(K, V) of pull i, valid for work enqueued on the current stream after this call."""
+        torch.cuda.current_stream(self.dev).wait_event(self.ev_copy.pop(i))
+        return self.stage[i % 2][0], self.stage[i % 2][1]
+
+    def release(self, i):
+        self.ev_free[i % 2] = torch.cuda.Event()
+        self.ev_free[i % 2].record(torch.cuda.current_stream(self.dev))
+
+    def finish(self):
+        self._barrier()       # nobody is still pulling from a buffer the next call will overwrite
 
 
 _p2p_states = {}
@@ -157,35 +192,16 @@ def _p2p_state(k, group):
     key = (id(group) if group is not None else 0, k.device.index, tuple(k.shape), k.dtype)
     st = _p2p_states.get(key)
     if st is None:
-        st = _p2p_states[key] = _P2PState(2 * k.numel() * k.element_size(), k, group)
+        st = _p2p_states[key] = _P2PState(k, group)
     return st
 
 
-def _ring_p2p(q, k, v, causal, zz, c, attn, merge, group, rank, world):
-    """The ring forward over the p2p transport (see the module docstring).  Returns the fp32 accumulator and the LSE."""
-    st = _p2p_state(k, group)
-    main = torch.cuda.current_stream(q.device)
+def _ring_pull(st, q, k, v, causal, zz, c, attn, merge, rank, world):
+    """The ring forward over a pull transport `st` (see _P2PState).  Returns the fp32 accumulator and the LSE."""
     kc, vc = k.contiguous(), v.contiguous()
-    half = st.nbytes // 2
-    # publish this rank's shard, then wait until every rank has published
-    st.copy(st.local, kc.data_ptr(), half, main)
-    st.copy(st.local + half, vc.data_ptr(), half, main)
-    st.barrier()
-    ev_start = torch.cuda.Event()
-    ev_start.record(main)
+    st.publish(kc, vc)
     # the remote shards this rank needs, in ring order (a causal ring with contiguous shards never looks at later ranks)
     remote = [src for _, src in ring_schedule(rank, world)[1:] if zz or not causal or src < rank]
-    ev_copy, ev_free = [None] * len(remote), [None, None]
-
-    def prefetch(i):
-        with torch.cuda.stream(st.side):
-            st.side.wait_event(ev_start)
-            if ev_free[i % 2] is not None:
-                st.side.wait_event(ev_free[i % 2])    # the kernels that read this staging buffer two steps ago are done
-            st.copy(st.stage[i % 2].data_ptr(), st.peer[remote[i]], st.nbytes, st.side)
-            ev_copy[i] = torch.cuda.Event()
-            ev_copy[i].record(st.side)
-
     acc = [[None, None], [None, None]]   # zig-zag: one accumulator per query chunk; otherwise acc[0]
 
     def accumulate(slot, o_s, lse_s):
@@ -200,16 +216,14 @@ def _ring_p2p(q, k, v, causal, zz, c, attn, merge, group, rank, world):
             accumulate(0, *attn(q, k_s, v_s, bool(causal and src == rank)))
 
     if remote:
-        prefetch(0)
+        st.prefetch(0, remote[0])
     compute(rank, kc, vc)                      # the local shard, while the first remote shard is on its way
     for i, src in enumerate(remote):
         if i + 1 < len(remote):
-            prefetch(i + 1)
-        main.wait_event(ev_copy[i])
-        compute(src, st.stage[i % 2][0], st.stage[i % 2][1])
-        ev_free[i % 2] = torch.cuda.Event()
-        ev_free[i % 2].record(main)
-    st.barrier()                               # nobody is still pulling from a buffer the next call will overwrite
+            st.prefetch(i + 1, remote[i + 1])
+        compute(src, *st.acquire(i, src))
+        st.release(i)
+    st.finish()
     if zz:
         return torch.cat([acc[0][0], acc[1][0]], dim=-2), torch.cat([acc[0][1], acc[1][1]], dim=-1)
     return acc[0][0], acc[0][1]
@@ -220,8 +234,8 @@ def ring_attention(q, k, v, causal=False, scale=None, group=None, zigzag=False, 
     """Sequence-partitioned forward.  q, k, v: this rank's shards [B, H, N/P, d] (or [B*H, N/P, d]), rank r holding
     sequence positions [r*N/P, (r+1)*N/P) — or, with zigzag=True (causal only), chunks r and 2P-1-r of 2P
     (zigzag_shard).  Returns this rank's shard of O in q's dtype and the fp32 LSE, in the same layout as q.
-    transport: "p2p" (copy-engine pulls from CUDA-IPC-mapped peer buffers; the default for CUDA tensors) or "nccl"
-    (send/recv rotation; the default for the CPU test seams).
+    transport: "p2p" (copy-engine pulls from CUDA-IPC-mapped peer buffers; the default for CUDA tensors), "nccl"
+    (send/recv rotation; the default for the CPU test seams), or an object with the pull-transport protocol of _P2PState.
 
     `_attn`, `_merge`, `_finalize` are test seams (the gloo/CPU tests inject the oracle to exercise the rotation and the
     merge without a GPU); the product path leaves them None and runs the CUDA kernels.
@@ -256,15 +270,17 @@ def ring_attention(q, k, v, causal=False, scale=None, group=None, zigzag=False, 
         return (_finalize(o) if _finalize else (api.cast_to_16(o, q.dtype) if (on_gpu and q.dtype != torch.float32) else o)), lse
     if transport is None:
         transport = "p2p" if (on_gpu and _attn is None) else "nccl"
-    if transport not in ("p2p", "nccl"):
+    if isinstance(transport, str) and transport not in ("p2p", "nccl"):
         raise ValueError(f"unknown ring transport {transport!r}")
-    if transport == "p2p":
-        if not on_gpu:
+    if transport != "nccl":
+        if transport == "p2p" and not on_gpu:
             raise ValueError("the p2p transport needs CUDA tensors")
-        o_acc, lse_acc = _ring_p2p(q, k, v, causal, zz, c, attn, merge, group, rank, world)
+        # a transport object (publish / prefetch / acquire / release / finish) is the CPU tests' stand-in for _P2PState
+        st = _p2p_state(k, group) if transport == "p2p" else transport
+        o_acc, lse_acc = _ring_pull(st, q, k, v, causal, zz, c, attn, merge, rank, world)
         if _finalize is not None:
             return _finalize(o_acc), lse_acc
-        return (api.cast_to_16(o_acc, q.dtype) if q.dtype != torch.float32 else o_acc), lse_acc
+        return (api.cast_to_16(o_acc, q.dtype) if (on_gpu and q.dtype != torch.float32) else o_acc), lse_acc
 
     nxt = dist.get_global_rank(group, (rank + 1) % world) if group is not None else (rank + 1) % world
     prv = dist.get_global_rank(group, (rank - 1) % world) if group is not None else (rank - 1) % world

@@ -362,6 +362,28 @@ def test_merge_partials_and_single_gpu_ring_emulation(fab, oracle, cuda_device):
     assert o_bf.dtype == torch.bfloat16 and np.abs(o_bf.float().cpu().numpy() - o_ref).max() < TOL_BF16
 
 
+def test_p2p_staging_buffer_and_copy_engine_entry(fab, cuda_device):
+    """The single-process half of the ring's p2p transport: fa_p2p_alloc returns a device buffer and a 64-byte IPC handle,
+    fa_copy_async moves bytes in and out of it on a side stream, fa_p2p_free releases it.  (Mapping the handle needs a
+    second process: scripts/multi_gpu_check.py, run by test_multi_gpu_sharding_and_ring_over_nccl on >= 2 GPUs.)"""
+    import ctypes
+
+    L = fab.lib()
+    src = torch.arange(1 << 20, dtype=torch.int32, device=cuda_device)
+    dst = torch.zeros_like(src)
+    nbytes = src.numel() * 4
+    ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+    assert L.fa_p2p_alloc(nbytes, ctypes.byref(ptr), handle) == 0 and ptr.value and any(handle.raw)
+    side = torch.cuda.Stream(device=cuda_device)
+    side.wait_stream(torch.cuda.current_stream())
+    assert L.fa_copy_async(ptr, ctypes.c_void_p(src.data_ptr()), nbytes, ctypes.c_void_p(side.cuda_stream)) == 0
+    assert L.fa_copy_async(ctypes.c_void_p(dst.data_ptr()), ptr, nbytes, ctypes.c_void_p(side.cuda_stream)) == 0
+    side.synchronize()
+    assert torch.equal(src, dst)
+    assert L.fa_p2p_free(ptr) == 0
+    assert L.fa_p2p_alloc(0, ctypes.byref(ptr), handle) == -1 and L.fa_copy_async(None, None, 16, None) == -1
+
+
 @pytest.mark.parametrize("dtype,d", [(torch.float32, 64), (torch.bfloat16, 128)])
 def test_strided_views_are_read_in_place(fab, cuda_device, dtype, d):
     """A slice of the sequence axis (strides != shape) goes into the TMA tensor maps as it is: same bits as the

@@ -150,3 +150,91 @@ def test_ring_attention_over_gloo(world, causal):
         assert err_l < 1e-12, (rank, err_l)
         covered = [i for (s, e) in counts for i in range(s, e)]
         assert covered == list(range(2))
+
+
+class _GatherPull:
+    """CPU stand-in for the p2p transport (flashattention_c_b200.ring._P2PState): publishing = all-gathering every rank's K/V
+    shard (on the GPU every owner's buffer is readable through its IPC mapping), a pull = indexing the gathered list.  It
+    checks the protocol `_ring_pull` must follow: staging buffer i % 2 is free when pull i starts, every pull is acquired
+    exactly once with the source it was started with, nothing is in flight at the end."""
+
+    def __init__(self):
+        self.busy, self.inflight, self.pulled = [None, None], {}, []
+
+    def publish(self, kc, vc):
+        world = dist.get_world_size()
+        self.k_all = [torch.empty_like(kc) for _ in range(world)]
+        self.v_all = [torch.empty_like(vc) for _ in range(world)]
+        dist.all_gather(self.k_all, kc)
+        dist.all_gather(self.v_all, vc)
+
+    def prefetch(self, i, src):
+        assert self.busy[i % 2] is None, f"staging buffer {i % 2} still in use by pull {self.busy[i % 2]}"
+        self.busy[i % 2] = i
+        self.inflight[i] = src
+
+    def acquire(self, i, src):
+        assert self.inflight.pop(i) == src
+        self.pulled.append(src)
+        return self.k_all[src], self.v_all[src]
+
+    def release(self, i):
+        assert self.busy[i % 2] == i
+        self.busy[i % 2] = None
+
+    def finish(self):
+        assert not self.inflight and self.busy == [None, None]
+        dist.barrier()
+
+
+def _pull_worker(rank, world, port, causal, zigzag, ret):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import flashattention_c_b200 as fab
+        from oracle import fa_oracle
+
+        B, H, N, d = 1, 2, 16 * 2 * world, 16
+        rng = np.random.default_rng(300)
+        q, k, v = (torch.from_numpy(rng.standard_normal((B, H, N, d), dtype=np.float32)) for _ in range(3))
+        scale = 0.25
+        attn, merge = _oracle_attn(scale)
+        if zigzag:
+            qs, ks, vs = (fab.zigzag_shard(t, rank, world).contiguous() for t in (q, k, v))
+        else:
+            n_loc = N // world
+            qs, ks, vs = (t[:, :, rank * n_loc:(rank + 1) * n_loc].contiguous() for t in (q, k, v))
+        tr = _GatherPull()
+        for _ in range(2):   # a second call reuses the transport object, as the cached GPU state is reused
+            o_loc, lse_loc = fab.ring_attention(qs, ks, vs, causal=causal, scale=scale, zigzag=zigzag, transport=tr, _attn=attn,
+                                                _merge=merge, _finalize=lambda o: o)
+        o_full, lse_full = fa_oracle.f64(q.numpy(), k.numpy(), v.numpy(), scale, causal)
+        if zigzag:
+            o_ref = fab.zigzag_shard(torch.from_numpy(o_full), rank, world).numpy()
+            lse_ref = fab.zigzag_shard(torch.from_numpy(lse_full).unsqueeze(-1), rank, world).squeeze(-1).numpy()
+        else:
+            o_ref, lse_ref = o_full[:, :, rank * n_loc:(rank + 1) * n_loc], lse_full[:, :, rank * n_loc:(rank + 1) * n_loc]
+        ret[rank] = (float(np.abs(o_loc.numpy() - o_ref).max()), float(np.abs(lse_loc.numpy() - lse_ref).max()), list(tr.pulled))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,causal,zigzag", [(2, False, False), (4, False, False), (4, True, False), (2, True, True), (4, True, True)])
+def test_pull_transport_schedule_over_gloo(world, causal, zigzag):
+    """The p2p ring's schedule (which owner is pulled in which step, prefetch one step ahead into a two-buffer ping-pong,
+    causal shard skipping, zig-zag step plan on pulled shards) with the transport replaced by a CPU stand-in."""
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_pull_worker, args=(world, port, causal, zigzag, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for rank in range(world):
+        err_o, err_l, pulled = ret[rank]
+        assert err_o < 1e-12 and err_l < 1e-12, (rank, err_o, err_l)
+        per_call = pulled[:len(pulled) // 2]
+        assert pulled == per_call * 2
+        if causal and not zigzag:
+            assert per_call == [(rank - s) % world for s in range(1, world) if (rank - s) % world < rank]   # earlier ranks only
+        else:
+            assert per_call == [(rank - s) % world for s in range(1, world)]                                   # every other owner, ring order
