@@ -1,6 +1,6 @@
 #!/bin/bash
-# Round-end GPU session: pytest -m gpu, smoke, bench (ours + reference arm), ncu launch list of the bench command,
-# ncu --set full captures of the C2 and C4 kernels (read back with scripts/ncu_summary.py).
+# Round-end GPU session: pytest -m gpu, smoke, bench (own arm + reference arm), ncu launch list of the bench command,
+# ncu --set full captures of the C2, C4 and fp32 d=128 (one-slot) kernels (read back with scripts/ncu_summary.py).
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 H=flashattention.c_b200/harness
 mkdir -p gpurun_out
@@ -18,9 +18,11 @@ cat gpurun_out/bench_ref.json >> $L
 echo "== ncu launch list" >> $L
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
    python bench.py --steps 3 --warmup 3 --no-cpu --no-extra > gpurun_out/bench_under_ncu.json 2>> $L
-echo "== ncu full (C2, C4 kernels)" >> $L
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:fa_fwd_sm100 -s 2 -c 1 -f -o gpurun_out/prof_c2 \
+echo "== ncu full (C2, fp32 d=128 one-slot, C4 kernels)" >> $L
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:fa_fwd_sm100 -s 2 -c 1 -f -o gpurun_out/prof_c2 \
    $H/fa_check f32 64 16 8192 0 0 2 0 >> $L 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:fa_fwd_sm100 -s 2 -c 1 -f -o gpurun_out/prof_c4 \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:fa_fwd_sm100 -s 2 -c 1 -f -o gpurun_out/prof_f32_d128 \
+   $H/fa_check f32 128 16 8192 0 0 2 0 >> $L 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:fa_fwd_sm100 -s 2 -c 1 -f -o gpurun_out/prof_c4 \
    $H/fa_check bf16 128 128 8192 0 0 2 0 >> $L 2>&1
-grep -v "^==PROF==" $L | tail -n 40
+grep -v "^==PROF==" $L | cut -c1-400 | tail -n 40
