@@ -267,7 +267,7 @@ def run_ours(args, torch, dist, rank, world, device):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/); None = not captured
-TRAFFIC_BYTES = {"C2": 115.6e6, "C4": 1058.4e6}   # dram__bytes_read+write per launch, profiles/r01_ncu_summary.md (v8 kernel)
+TRAFFIC_BYTES = {"C2": 117.4e6, "C4": 1057.8e6}   # dram__bytes_read+write per launch, profiles/r01_ncu_summary.md (v9 kernel)
 
 
 def other_configs(torch, fab, device, flush, peaks):
