@@ -22,6 +22,6 @@ from .api import (  # noqa: F401
     load_extension,
     merge_partials,
 )
-from .ring import bh_shard_range, ring_attention, sharded_attention, zigzag_shard, zigzag_step_plan, zigzag_unshard  # noqa: F401
+from .ring import bh_shard_range, ring_attention, ring_p2p_release, sharded_attention, zigzag_shard, zigzag_step_plan, zigzag_unshard  # noqa: F401
 
 __version__ = "0.1.0"

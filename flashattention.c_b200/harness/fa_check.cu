@@ -1,10 +1,11 @@
 // fa_check.cu — torch-free correctness + timing harness over the C-ABI (include/fa_b200.h).
-//   ./fa_check <f32|bf16> <d> <B*H> <N> <causal 0|1> <scale (0 = 1/sqrt(d))> [reps=20] [check_simt=1]
+//   ./fa_check <f32|bf16|f16> <d> <B*H> <N> <causal 0|1> <scale (0 = 1/sqrt(d))> [reps=20] [check_simt=1]
 // For each run it (1) launches the tcgen05 path and the SIMT path on the same seeded N(0,1) inputs and
 // reports their max-abs difference over the whole tensor, (2) checks sampled rows of both against an fp64
 // host evaluation of softmax(scale*q.K^T [+causal]) V, (3) times the tcgen05 path with CUDA events
 // (L2 flushed between repetitions; FA_CHECK_TIME_IMPL=2 times the CUDA-core kernel instead) and prints one JSON line.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -36,13 +37,15 @@ static inline double urand() {
 static inline float nrand() { return (float)(sqrt(-2.0 * log(urand())) * cos(6.283185307179586 * urand())); }
 
 static float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+static float f16_round(float x) { return __half2float(__float2half_rn(x)); }
 
 int main(int argc, char** argv) {
   if (argc < 7) {
-    printf("usage: %s f32|bf16 d BH N causal scale [reps] [check_simt]\n", argv[0]);
+    printf("usage: %s f32|bf16|f16 d BH N causal scale [reps] [check_simt]\n", argv[0]);
     return 1;
   }
-  const bool bf16 = !strcmp(argv[1], "bf16");
+  const bool f16 = !strcmp(argv[1], "f16");
+  const bool bf16 = !strcmp(argv[1], "bf16") || f16;   // "16-bit operands" from here on; f16 picks the conversions
   const int d = atoi(argv[2]);
   const int64_t BH = atoll(argv[3]), N = atoll(argv[4]);
   const int causal = atoi(argv[5]);
@@ -57,17 +60,20 @@ int main(int argc, char** argv) {
   for (auto& x : hk) x = nrand();
   for (auto& x : hv) x = nrand();
   if (bf16) {
-    for (auto& x : hq) x = bf16_round(x);
-    for (auto& x : hk) x = bf16_round(x);
-    for (auto& x : hv) x = bf16_round(x);
+    for (auto& x : hq) x = f16 ? f16_round(x) : bf16_round(x);
+    for (auto& x : hk) x = f16 ? f16_round(x) : bf16_round(x);
+    for (auto& x : hv) x = f16 ? f16_round(x) : bf16_round(x);
   }
   auto upload = [&](const std::vector<float>& h, void** dptr) -> int {
     CK(cudaMalloc(dptr, n_el * es));
     if (!bf16) {
       CK(cudaMemcpy(*dptr, h.data(), n_el * 4, cudaMemcpyHostToDevice));
     } else {
-      std::vector<__nv_bfloat16> t(n_el);
-      for (size_t i = 0; i < n_el; ++i) t[i] = __float2bfloat16_rn(h[i]);
+      std::vector<uint16_t> t(n_el);
+      for (size_t i = 0; i < n_el; ++i) {
+        if (f16) { const __half x = __float2half_rn(h[i]); memcpy(&t[i], &x, 2); }
+        else { const __nv_bfloat16 x = __float2bfloat16_rn(h[i]); memcpy(&t[i], &x, 2); }
+      }
       CK(cudaMemcpy(*dptr, t.data(), n_el * 2, cudaMemcpyHostToDevice));
     }
     return 0;
@@ -85,7 +91,7 @@ int main(int argc, char** argv) {
   fa_params p;
   memset(&p, 0, sizeof(p));
   p.q = dq; p.k = dk; p.v = dv; p.batch = 1; p.heads = BH; p.n_q = N; p.n_k = N; p.head_dim = d;
-  p.dtype = bf16 ? FA_BF16 : FA_F32; p.causal = causal; p.scale = scale;
+  p.dtype = f16 ? FA_F16 : (bf16 ? FA_BF16 : FA_F32); p.causal = causal; p.scale = scale;
   p.q_stride_n = p.k_stride_n = p.v_stride_n = p.o_stride_n = d;
   p.q_stride_h = p.k_stride_h = p.v_stride_h = p.o_stride_h = N * d;
   p.q_stride_b = p.k_stride_b = p.v_stride_b = p.o_stride_b = BH * N * d;
@@ -105,9 +111,12 @@ int main(int argc, char** argv) {
     h.resize(n_el);
     if (!bf16) { CK(cudaMemcpy(h.data(), dptr, n_el * 4, cudaMemcpyDeviceToHost)); }
     else {
-      std::vector<__nv_bfloat16> t(n_el);
+      std::vector<uint16_t> t(n_el);
       CK(cudaMemcpy(t.data(), dptr, n_el * 2, cudaMemcpyDeviceToHost));
-      for (size_t i = 0; i < n_el; ++i) h[i] = __bfloat162float(t[i]);
+      for (size_t i = 0; i < n_el; ++i) {
+        if (f16) { __half x; memcpy(&x, &t[i], 2); h[i] = __half2float(x); }
+        else { __nv_bfloat16 x; memcpy(&x, &t[i], 2); h[i] = __bfloat162float(x); }
+      }
     }
     return 0;
   };

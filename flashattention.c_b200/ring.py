@@ -185,7 +185,31 @@ class _P2PState:
         self._barrier()       # nobody is still pulling from a buffer the next call will overwrite
 
 
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (collective in spirit: call it on every rank, after a barrier)."""
+        import ctypes
+
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        for r, pp in enumerate(self.peer):
+            if r != rank and pp:
+                self.L.fa_p2p_close(ctypes.c_void_p(pp))
+        if self.local:
+            self.L.fa_p2p_free(ctypes.c_void_p(self.local))
+        self.peer, self.local = [], None
+
+
 _p2p_states = {}
+
+
+def ring_p2p_release(group=None):
+    """Drop the cached p2p transport state (exported buffers, peer mappings, staging buffers) of `group` — or of every group
+    with group=None.  Call it on every rank before destroying the process group; the next ring_attention call rebuilds it."""
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if dist.is_initialized():
+        dist.barrier(group)       # no peer is still pulling from a buffer that is about to be freed
+    for key in [k for k in _p2p_states if group is None or k[0] == id(group)]:
+        _p2p_states.pop(key).close()
 
 
 def _p2p_state(k, group):

@@ -156,6 +156,7 @@ def main():
     if rank == 0:
         for o in out:
             print(json.dumps(o), flush=True)
+    fab.ring_p2p_release()
     dist.destroy_process_group()
 
 
