@@ -77,6 +77,28 @@
 #ifndef FA_OPT_RELEASE_IN_STEP
 #define FA_OPT_RELEASE_IN_STEP 1  // K/V ring slots released from inside slot B's step (one elect block less per K/V step)
 #endif
+#ifndef FA_OPT_EARLY_HI
+#define FA_OPT_EARLY_HI 0    // 16-bit instances: P (two values per column) only covers columns [0, 64) of S, and once the first piece
+                             // of P has arrived every S column is in registers — so the upper half of the next Q*K^T (keys 64..127
+                             // -> columns [64, 128)) is issued right behind the first piece's P*V instead of after the second's
+#endif
+#ifndef FA_OPT_ROLL_MMA
+#define FA_OPT_ROLL_MMA 0    // 1: the k-step loops of the MMA warp stay rolled (smaller code for a warp that shares its instruction
+                             // cache with the unrolled exp loops of the softmax warps)
+#endif
+#ifndef FA_OPT_ROLL_STEP
+#define FA_OPT_ROLL_STEP 0   // 1: one copy of the per-slot step code, looped over the two slots
+#endif
+#if FA_OPT_ROLL_MMA
+#define FA_MMA_UNROLL _Pragma("unroll 1")
+#else
+#define FA_MMA_UNROLL _Pragma("unroll")
+#endif
+#if FA_OPT_ROLL_STEP
+#define FA_STEP_UNROLL _Pragma("unroll 1")
+#else
+#define FA_STEP_UNROLL _Pragma("unroll")
+#endif
 #ifndef FA_OPT_SPLIT_KEYS
 #define FA_OPT_SPLIT_KEYS 64  // (96 measured 2-3% slower: profiles/r01_ab_tf32_comp.log) P is handed to the MMA warp in two pieces: keys [0, FA_OPT_SPLIT_KEYS) and the rest (64 or 96)
 #endif
@@ -180,6 +202,7 @@ struct FwdTraits {
   static constexpr int kP1Cols = (kBlockN - kSplitKeys) * kInSize / 4;   // TMEM columns of the second piece of P
   static constexpr int kTmemP1 = 256 + 2 * kHeadDim;                      // + kP1Cols*t (kEarlyS only)
   static constexpr bool kSplitP = (FA_OPT_SPLITP != 0) && (kDChunks > 1 || FA_OPT_SPLITP_NARROW != 0);   // P delivered in two pieces
+  static constexpr bool kEarlyHi = (FA_OPT_EARLY_HI != 0) && kSplitP && !kTF32 && (FA_OPT_EARLY_S == 0);
   static constexpr bool kEarlyS = (FA_OPT_EARLY_S != 0) && kSplitP && (256 + 2 * kHeadDim + 2 * kP1Cols <= 512);
   static_assert(kDChunks == 1 || kDChunks == 2 || kDChunks == 4, "tile row must be 128, 256 or 512 bytes");
   static_assert(256 + kSlots * kHeadDim <= 512, "TMEM budget");
@@ -449,10 +472,23 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const uint64_t qd = sdesc_at(hi_kmajor, sQ + T::q_tile(qbuf) * T::kTileBytes);
       const uint64_t kd = sdesc_at(hi_kmajor, sKV + buf * T::kTileBytes);
       const uint32_t d = tmem_base + T::kTmemS + t * kBlockN;
-#pragma unroll
+      FA_MMA_UNROLL
       for (int kk = 0; kk < kKStepsS; ++kk) {
         const uint32_t off16 = ((kk >> 2) * kChunkBytes + (kk & 3) * 32) >> 4;
         mma_ss<kTF32>(d, qd + off16, kd + off16, idesc_s, kk > 0 ? 1u : 0u);
+      }
+    };
+    // one 64-key half of S_t = Q_t K^T: keys [64*half, 64*half + 64) of the tile -> S columns [64*half, +64) (kEarlyHi).
+    // K is K-major: key row r of a 128-byte column chunk sits at r * 128 bytes (swizzled inside 1024-byte groups of 8 rows)
+    constexpr uint32_t idesc_s_half = make_idesc(kFmt, 0, kBlockM, kBlockN / 2);
+    auto issue_s_half = [&](int t, int qbuf, int buf, int half) {
+      const uint64_t qd = sdesc_at(hi_kmajor, sQ + T::q_tile(qbuf) * T::kTileBytes);
+      const uint64_t kd = sdesc_at(hi_kmajor, sKV + buf * T::kTileBytes + half * (kBlockN / 2) * 128);
+      const uint32_t d = tmem_base + T::kTmemS + t * kBlockN + half * (kBlockN / 2);
+      FA_MMA_UNROLL
+      for (int kk = 0; kk < kKStepsS; ++kk) {
+        const uint32_t off16 = ((kk >> 2) * kChunkBytes + (kk & 3) * 32) >> 4;
+        mma_ss<kTF32>(d, qd + off16, kd + off16, idesc_s_half, kk > 0 ? 1u : 0u);
       }
     };
     // P*V for k-steps [ks0, ks1) of the 128-key tile; A = P_t read from TMEM (it aliases S_t)
@@ -462,7 +498,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       // P aliases S; with kEarlyS the second piece (k-steps >= kKStepsSplit) has its own columns
       const bool own = T::kEarlyS && ks0 >= kKStepsSplit;
       const uint32_t a = own ? tmem_base + T::kTmemP1 + t * T::kP1Cols - kKStepsSplit * 8 : tmem_base + T::kTmemS + t * kBlockN;
-#pragma unroll
+      FA_MMA_UNROLL
       for (int ks = ks0; ks < ks1; ++ks) {
         mma_ts<kTF32>(d, a + ks * 8, vd + static_cast<uint32_t>(ks * (T::kUmmaK * 128 / 16)), idesc_pv,
                       (accumulate || ks > 0) ? 1u : 0u);
@@ -529,7 +565,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mbar_wait(bar_p + 16 * t, par, TAG_P_FULL);            // keys [0, 64) of P are in TMEM
         tc_fence_after();
         FA_TRACE_AT(2 + t, g, 1);
-        if (elect_one_sync()) issue_pv(t, vbuf, j > 0, 0, kKStepsSplit);
+        if (elect_one_sync()) {
+          issue_pv(t, vbuf, j > 0, 0, kKStepsSplit);
+          if (T::kEarlyHi && !last) issue_s_half(t, qbuf, kbuf, 1);   // every column of S_t(j) is in registers by now
+        }
         __syncwarp();
         FA_TRACE_AT(2 + t, g, 2);
       }
@@ -542,7 +581,8 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (last) {
           tc_commit(bar_o + 8 * t);
         } else {
-          issue_s(t, qbuf, kbuf);
+          if constexpr (T::kEarlyHi) issue_s_half(t, qbuf, kbuf, 0);   // columns [0, 64): where P_t(j) was
+          else issue_s(t, qbuf, kbuf);
           tc_commit(bar_s + 8 * t);
           if (release) tc_commit(bar_empty + 8 * kbuf);
         }
@@ -607,8 +647,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           // P V(j) and Q K^T(j+1) when slot B is the longer one (n1 == n_max: every causal and every full item) — released
           // from inside its step, in the elect block that issues those MMAs — else in a block of their own
           const bool rel_in_b = FA_OPT_RELEASE_IN_STEP != 0 && w.n1 == w.n_max;
-          if (j < w.n0) step(0, j, j == w.n0 - 1, set * 2, vbuf, kbuf, false);
-          if (j < w.n1) step(1, j, j == w.n1 - 1, set * 2 + 1, vbuf, kbuf, rel_in_b);
+          FA_STEP_UNROLL
+          for (int t = 0; t < 2; ++t)
+            if (j < w.n(t)) step(t, j, j == w.n(t) - 1, set * 2 + t, vbuf, kbuf, t == 1 && rel_in_b);
           if (!rel_in_b) {
             if (elect_one_sync()) {
               tc_commit(bar_empty + 8 * vbuf);
