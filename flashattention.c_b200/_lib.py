@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = [
     "run_flash_tiled_coarse", "run_flash_tiled_coarse_causal", "attention_forward6", "attention_forward",
     "fa_strerror", "fa_last_cuda_error", "fa_last_impl", "fa_version", "fa_launch_count",
     "fa_watchdog_info",
-    "fa_p2p_alloc", "fa_p2p_open", "fa_p2p_close", "fa_p2p_free", "fa_copy_async",
+    "fa_p2p_alloc", "fa_p2p_open", "fa_p2p_close", "fa_p2p_free", "fa_copy_async", "fa_query_instance",
 ]
 
 
@@ -77,6 +77,8 @@ def lib() -> ctypes.CDLL:
         L.fa_p2p_free.restype = ctypes.c_int
         L.fa_copy_async.argtypes = [vp, vp, i64, vp]
         L.fa_copy_async.restype = ctypes.c_int
+        L.fa_query_instance.argtypes = [i32, i32]
+        L.fa_query_instance.restype = ctypes.c_int
         L.fa_strerror.argtypes = [ctypes.c_int]
         L.fa_strerror.restype = ctypes.c_char_p
         L.fa_last_cuda_error.argtypes = []

@@ -91,7 +91,7 @@ def build_oracle(force=False, with_ref=True):
     targets = ["oracle"]
     if with_ref and Path("/root/reference/src/flashattention.cu").exists():
         targets.append("ref")
-    _run(["make", "-C", ROOT / "oracle", *targets] + (["-B"] if force else []))
+    _run(["make", f"-j{min(4, os.cpu_count() or 1)}", "-C", ROOT / "oracle", *targets] + (["-B"] if force else []))
 
 
 def build_all(force=False, torch_ext=True, with_ref=True):

@@ -416,6 +416,17 @@ const char* fa_strerror(int status) {
   }
 }
 
+int fa_query_instance(int32_t dtype, int32_t head_dim) {
+  if ((dtype != FA_F32 && dtype != FA_BF16 && dtype != FA_F16) || head_dim <= 0) return FA_ERR_INVALID_ARG;
+  fa_params p;
+  memset(&p, 0, sizeof(p));
+  p.dtype = dtype;
+  p.head_dim = head_dim;
+  const int di = tc_instance_dim(&p);
+  if (di) return di;
+  return (head_dim <= fa::kSimtMaxD && head_dim % 8 == 0) ? 0 : FA_ERR_UNSUPPORTED;
+}
+
 int fa_forward_ex(const fa_params* p, void* stream) {
   if (!p || !p->q || !p->k || !p->v || !p->o) return FA_ERR_INVALID_ARG;
   if (p->batch <= 0 || p->heads <= 0 || p->n_q <= 0 || p->n_k <= 0 || p->head_dim <= 0) return FA_ERR_INVALID_ARG;

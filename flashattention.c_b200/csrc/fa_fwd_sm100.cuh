@@ -32,7 +32,13 @@
 // (profiles/r01_ab_issuer_modes_session9.log).
 //
 // TMEM columns (512 allocated): S_A [0,128)  S_B [128,256)  O_A [256,256+d)  O_B [256+d, 256+2d).
-// P aliases S: bf16 path packs two bf16 per column into S cols [0,64); tf32 path overwrites S in place.
+// P aliases S: the 16-bit paths (bf16, fp16) pack two values per column into S cols [0,64); tf32 overwrites S in place.
+//
+// Instances: tile rows of 128, 256 or 512 bytes (fp32 d = 32 / 64 / 128, 16-bit d = 64 / 128 / 256).  The 512-byte-row
+// instances are "one-slot" (FwdTraits::kSlots == 1): one Q tile and a two-tile K/V ring fill SMEM, every item is a 128-row item
+// on slot A, slot B's warps idle (and O_B's columns stay unused, which is what lets d = 256 fit).  Head dims below an
+// instance run on it unchanged: the tensor maps carry the true head dim, TMA zero-fills the missing columns on load and
+// clips them on store.
 //
 // SMEM (dynamic, 1024-B aligned): kQSets x (Q_A | Q_B) (Q_A only with 512-byte rows) | ring of NBUF K/V tiles | barriers | work queue | (m, l)
 // exchange.  Every tile is DCHUNKS boxes of [128 rows x 128 bytes] in the SWIZZLE_128B layout that TMA writes and

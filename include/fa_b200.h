@@ -155,6 +155,14 @@ void attention_forward6(float* out, const float* inp, int B, int T, int C, int N
 void attention_forward(int kernel_num, float* out, float* vaccum, float* qkvr, float* preatt, float* att,
                        const float* inp, int B, int T, int C, int NH, const int block_size);
 
+/*
+ * fa_query_instance — which kernel serves (dtype, head_dim); needs no device.  > 0: the tcgen05 kernel instance (its head dim:
+ * 32 / 64 / 128 for fp32, 64 / 128 / 256 for bf16 and fp16; a smaller head_dim is zero-padded onto it by TMA); 0: the CUDA-core
+ * kernel (fp32 head dims in (128, 256], multiples of 8); < 0: FA_ERR_UNSUPPORTED / FA_ERR_INVALID_ARG.  The reference fixes the
+ * head dim at compile time (`# define d 64`, src/flashattention.cu:15) and supports nothing else.
+ */
+int fa_query_instance(int32_t dtype, int32_t head_dim);
+
 /* diagnostics */
 const char* fa_strerror(int status);
 const char* fa_last_cuda_error(void); /* text of the last CUDA failure seen by this thread ("" if none) */

@@ -88,6 +88,22 @@ def test_version_and_strerror(fab):
     assert L.fa_strerror(-12345) == b"unknown status"
 
 
+def test_kernel_dispatch_table(fab):
+    """fa_query_instance (host only): fp32 d <= 32 / 64 / 128 and 16-bit d <= 64 / 128 / 256 map onto the tcgen05 instances
+    (smaller head dims zero-padded by TMA), fp32 (128, 256] goes to the CUDA-core kernel, the rest is refused."""
+    from flashattention_c_b200 import _lib
+
+    q = fab.lib().fa_query_instance
+    F32, BF16, F16 = _lib.FA_F32, _lib.FA_BF16, _lib.FA_F16
+    assert [q(F32, d) for d in (4, 8, 32, 36, 64, 68, 96, 128)] == [32, 32, 32, 64, 64, 128, 128, 128]
+    assert [q(F32, d) for d in (136, 256)] == [0, 0]                       # CUDA-core kernel
+    assert q(F32, 6) == -4 and q(F32, 132) == -4 and q(F32, 264) == -4      # rows not 16-byte aligned / too wide
+    for dt in (BF16, F16):
+        assert [q(dt, d) for d in (8, 64, 72, 128, 136, 256)] == [64, 64, 128, 128, 256, 256]
+        assert q(dt, 12) == -4 and q(dt, 264) == -4
+    assert q(7, 64) == -1 and q(F32, 0) == -1
+
+
 def test_invalid_arguments_are_rejected_before_touching_a_device(fab):
     L = fab.lib()
     assert L.fa_forward(None, None, None, None, None, 1, 1, 16, 16, 64, 1.0, 0, 0, None) == -1   # null pointers
