@@ -124,6 +124,14 @@
 #ifndef FA_POLY_DEN_TF32
 #define FA_POLY_DEN_TF32 4
 #endif
+// The 128-byte-row instances (fp32 d <= 32, 16-bit d <= 64) leave the tensor pipe mostly idle and run both slots' softmaxes
+// side by side, so their MUFU / FMA balance is tuned separately.
+#ifndef FA_POLY_NUM_NARROW
+#define FA_POLY_NUM_NARROW 1
+#endif
+#ifndef FA_POLY_DEN_NARROW
+#define FA_POLY_DEN_NARROW 4
+#endif
 // -DFA_TRACE=1 builds a timeline-tracing kernel: CTA 0 records clock64() at every pipeline hand-off of its first
 // kTraceSteps KV tiles into FwdParams::trace ([role 0..3][step][slot 0..7]); see scripts/trace_report.py.
 #ifndef FA_TRACE
@@ -196,8 +204,8 @@ struct FwdTraits {
   static constexpr bool kPacked = (FA_OPT_F2 != 0) && (!kTF32 || kComp);   // FFMA2 / FADD2 forms in the exp loop
   static constexpr int kSplitKeys = FA_OPT_SPLIT_KEYS;
   static_assert(kSplitKeys == 64 || kSplitKeys == 96, "P split point");
-  static constexpr int kPolyNum = kTF32 ? FA_POLY_NUM_TF32 : FA_POLY_NUM_BF16;   // polynomial exp2 on kPolyNum of every
-  static constexpr int kPolyDen = kTF32 ? FA_POLY_DEN_TF32 : FA_POLY_DEN_BF16;   // kPolyDen element pairs (packed path only)
+  static constexpr int kPolyNum = kDChunks == 1 ? FA_POLY_NUM_NARROW : (kTF32 ? FA_POLY_NUM_TF32 : FA_POLY_NUM_BF16);   // polynomial exp2 on kPolyNum of
+  static constexpr int kPolyDen = kDChunks == 1 ? FA_POLY_DEN_NARROW : (kTF32 ? FA_POLY_DEN_TF32 : FA_POLY_DEN_BF16);   // every kPolyDen element pairs (packed path only)
   static constexpr int kSmemData = (kSlots * kQSets + kNBuf) * kTileBytes;
   static constexpr int kNumBarriers = 4 * kQSets /*q full, q free*/ + 2 * kNBuf + 2 /*s_full*/ + 4 /*p_full halves*/ +
                                       2 /*o_final*/ + 2 /*o_free*/ + 2 * kWorkQueue + 2 /*pv1 done*/;
