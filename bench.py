@@ -1,12 +1,14 @@
 #!/usr/bin/env python
 """bench.py — the driver's measurement contract for the FlashAttention-forward hot path.
 
-    python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--workload C2|C1|C3|C4]
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--workload C2|C1|C3|C4|C5]
 
 One "step" = one forward pass O = softmax(QK^T/sqrt(d)) V over one batch of synthetic N(0,1) inputs.
 Default workload = BASELINE.json configs[1] (the README headline shape): B=2 H=8 d=64 N=8192, fp32 in HBM,
 tf32 tensor-core contractions.  With N > 1 ranks (torchrun, one process per GPU) the B x H axis is sharded with no
 data-path collective and per-GPU work is fixed ("weak"): every rank runs the same 16-head workload.
+
+--workload C5 is the ring-attention config (B=1 H=32 d=128 N=131072 bf16, sequence split over the ranks, strong scaling).
 
 Prints ONE JSON line on rank 0:
   value      TFLOP/s, whole job, kernel timed with CUDA events on the launch stream, inputs resident in HBM,
@@ -289,13 +291,90 @@ def other_configs(torch, fab, device, flush, peaks):
     return res
 
 
+def run_ring(args, torch, dist, rank, world, device):
+    """--workload C5: B=1 H=32 d=128 N=131072 bf16, the sequence split over the ranks (ring attention; one GPU: the plain
+    forward over the whole sequence).  Total work is fixed ("strong" scaling): value = 4*H*N^2*d / max-over-ranks time."""
+    import flashattention_c_b200 as fab
+
+    H, N, d = 32, 131072, 128
+    n_loc = N // world
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    q, k, v = (torch.randn(1, H, n_loc, d, device=device, generator=g).to(torch.bfloat16) for _ in range(3))
+    fn = lambda: fab.ring_attention(q, k, v, causal=False)   # noqa: E731  (p2p transport: copy-engine pulls over NVLink)
+    for _ in range(args.warmup):
+        o, _lse = fn()
+    torch.cuda.synchronize()
+    assert fab.last_impl() == fab.FA_IMPL_TCGEN05
+    sampler = ClockSampler(torch.cuda.current_device())
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = fab.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    launches = fab.launch_count() - launches0
+    total_ms = e0.elapsed_time(e1)
+    # e2e: this rank's shards from pinned host memory, the ring forward, this rank's O shard back to pinned host memory
+    hq, hk, hv = (t.cpu().pin_memory() for t in (q, k, v))
+    ho = torch.empty_like(hq).pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dq, dk, dv = (t.to(device, non_blocking=True) for t in (hq, hk, hv))
+        o, _lse = fab.ring_attention(dq, dk, dv, causal=False)
+        ho.copy_(o, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = t.tolist()
+    if rank != 0:
+        return None
+    fl = 4.0 * H * float(N) * N * d
+    ms_per_step = total_ms / args.steps
+    peaks = load_peaks()
+    achieved = fl / world / (ms_per_step * 1e-3) * 1e-12       # per GPU
+    shard_bytes = q.numel() * 2
+    return {
+        "metric": "fwd attention TFLOP/s (C5: B1 H32 d128 N131072 bf16, ring)", "value": round(fl / (ms_per_step * 1e-3) * 1e-12, 1),
+        "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"C5: B=1 H={H} d={d} N={N} bf16 non-causal, scale=1/sqrt(d); sequence split over {world} GPU(s), "
+                               f"{n_loc} rows per GPU; K/V shards pulled from their owners by the copy engines (p2p transport) under the kernel",
+                   "l2": "inputs larger than L2 (K+V shard per step: %d MB)" % (2 * shard_bytes >> 20),
+                   "flops_per_step_total": fl, "kv_bytes_pulled_per_gpu_per_step": 2 * shard_bytes * (world - 1)},
+        "e2e": {"value": round(fl / (e2e_s / e2e_steps) * 1e-12, 1), "unit": "TFLOP/s", "ms_per_step": round(e2e_s / e2e_steps * 1e3, 3),
+                "h2d_bytes_per_step": 3 * shard_bytes * world, "d2h_bytes_per_step": shard_bytes * world, "steps": e2e_steps,
+                "api": "ring_attention on this rank's shards copied from / to pinned host memory"},
+        "gpu_launches": launches,
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": round(peaks["bf16"], 1), "unit": "TFLOP/s",
+                     "frac": round(achieved / peaks["bf16"], 4), "traffic": None, "peak_source": peaks["src"] + " bf16_tflops (per GPU)",
+                     "kernel": "fa_fwd_sm100_kernel (bf16 d=128, fp32 partial output) x ring steps + fa_merge_kernel"},
+    }
+
+
 def run_reference(args, torch, rank, world, device):
     """The reference arm: its own forward(Q,K,V,causal) (scale fixed at 1.0 inside, src/flashattention.cu:593)."""
     if rank != 0:
         return None
     from oracle import fa_oracle
 
-    B, H, N, d, dtype = WORKLOADS[args.workload]
+    long_seq = args.workload == "C5"     # one forward of the reference kernel takes ~15 s at N = 131072: one warm-up, one step
+    B, H, N, d, dtype = (1, 32, 131072, 128, "bf16") if long_seq else WORKLOADS[args.workload]
     fl = flops_of(B, H, N, d)
     base = {"metric": "fwd attention TFLOP/s (B2 H8 d64 N8192)" if args.workload == "C2" else f"fwd attention TFLOP/s ({args.workload})",
             "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
@@ -306,8 +385,8 @@ def run_reference(args, torch, rank, world, device):
         hosts = [torch.randn(B * H, N, d, generator=g).pin_memory() for _ in range(3)]
         q, k, v = (h.to(device) for h in hosts)
         flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
-        steps = max(1, min(args.steps, 10))
-        warm = max(1, min(args.warmup, 3))
+        steps = 1 if long_seq else max(1, min(args.steps, 10))
+        warm = 1 if long_seq else max(1, min(args.warmup, 3))
         ms = time_kernel(torch, lambda: ext.forward(q, k, v, False), steps, warm, flush)
         ms_per_step = sum(ms) / len(ms)
         o_host = torch.empty(B * H, N, d).pin_memory()
@@ -357,7 +436,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS) + ["C5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the other_configs leg")
     args = ap.parse_args()
@@ -382,7 +461,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     try:
-        line = run_ours(args, torch, dist, rank, world, device) if args.impl == "ours" else run_reference(args, torch, rank, world, device)
+        if args.impl == "ours" and args.workload == "C5":
+            line = run_ring(args, torch, dist, rank, world, device)
+        elif args.impl == "ours":
+            line = run_ours(args, torch, dist, rank, world, device)
+        else:
+            line = run_reference(args, torch, rank, world, device)
         if line is not None:
             print(json.dumps(line), flush=True)
     finally:
