@@ -56,8 +56,9 @@ def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         j = json.loads(p.read_text())
-        return {"bf16": float(j["bf16_tflops"]), "hbm": float(j["hbm_gbs"]), "src": "MEASURED_PEAKS.json"}
-    return {"bf16": 1590.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+        return {"bf16": float(j["bf16_tflops"]), "bf16_sustained": float(j.get("bf16_tflops_sustained", j["bf16_tflops"])),
+                "hbm": float(j["hbm_gbs"]), "src": "MEASURED_PEAKS.json"}
+    return {"bf16": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler(threading.Thread):
@@ -361,8 +362,12 @@ def run_ring(args, torch, dist, rank, world, device):
                 "api": "ring_attention on this rank's shards copied from / to pinned host memory"},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
-        "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": round(peaks["bf16"], 1), "unit": "TFLOP/s",
-                     "frac": round(achieved / peaks["bf16"], 4), "traffic": None, "peak_source": peaks["src"] + " bf16_tflops (per GPU)",
+        # a step is hundreds of milliseconds of back-to-back tensor work under the power cap: the sustained cuBLAS figure is the
+        # denominator (the burst one is given beside it)
+        "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": round(peaks["bf16_sustained"], 1), "unit": "TFLOP/s",
+                     "frac": round(achieved / peaks["bf16_sustained"], 4), "traffic": None,
+                     "peak_source": peaks["src"] + " bf16_tflops_sustained (per GPU; long step under the power cap)",
+                     "frac_of_burst_peak": round(achieved / peaks["bf16"], 4),
                      "kernel": "fa_fwd_sm100_kernel (bf16 d=128, fp32 partial output) x ring steps + fa_merge_kernel"},
     }
 
