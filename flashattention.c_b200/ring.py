@@ -184,18 +184,21 @@ class _P2PState:
     def finish(self):
         self._barrier()       # nobody is still pulling from a buffer the next call will overwrite
 
-
-    def close(self):
-        """Unmap the peers' buffers and free this rank's (collective in spirit: call it on every rank, after a barrier)."""
+    def unmap_peers(self):
         import ctypes
 
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         for r, pp in enumerate(self.peer):
             if r != rank and pp:
                 self.L.fa_p2p_close(ctypes.c_void_p(pp))
+        self.peer = []
+
+    def free_local(self):
+        import ctypes
+
         if self.local:
             self.L.fa_p2p_free(ctypes.c_void_p(self.local))
-        self.peer, self.local = [], None
+        self.local = None
 
 
 _p2p_states = {}
@@ -203,13 +206,20 @@ _p2p_states = {}
 
 def ring_p2p_release(group=None):
     """Drop the cached p2p transport state (exported buffers, peer mappings, staging buffers) of `group` — or of every group
-    with group=None.  Call it on every rank before destroying the process group; the next ring_attention call rebuilds it."""
+    with group=None.  Collective: call it on every rank, before destroying the process group; the next ring_attention call
+    rebuilds the state.  Order: nobody pulls any more -> every rank unmaps its peers' buffers -> every rank frees its own (an
+    exported buffer must not be freed while another process still has it mapped)."""
+    keys = [k for k in _p2p_states if group is None or k[0] == (id(group) if group is not None else 0)]
     if torch.cuda.is_available():
         torch.cuda.synchronize()
     if dist.is_initialized():
-        dist.barrier(group)       # no peer is still pulling from a buffer that is about to be freed
-    for key in [k for k in _p2p_states if group is None or k[0] == id(group)]:
-        _p2p_states.pop(key).close()
+        dist.barrier(group)
+    for key in keys:
+        _p2p_states[key].unmap_peers()
+    if dist.is_initialized():
+        dist.barrier(group)
+    for key in keys:
+        _p2p_states.pop(key).free_local()
 
 
 def _p2p_state(k, group):
