@@ -11,10 +11,11 @@ LIB_PATH = PKG_DIR / "libfa_b200.so"
 FA_F32, FA_BF16, FA_F16 = 0, 1, 2
 FA_IMPL_AUTO, FA_IMPL_TCGEN05, FA_IMPL_SIMT = 0, 1, 2
 FA_FLAG_BATCH_INVARIANT = 1
+FA_FLAG_PRECISE = 2
 
 # every symbol include/fa_b200.h declares (tests check that the built library exports all of them)
 EXPORTED_SYMBOLS = [
-    "fa_forward", "fa_forward_ex", "fa_forward_packed_qkv", "fa_forward_host", "fa_merge_partials", "fa_cast_f32", "fa_cast_f32_to_bf16",
+    "fa_forward", "fa_forward_ex", "fa_forward_packed_qkv", "fa_forward_packed_qkv_ex", "fa_forward_host", "fa_merge_partials", "fa_cast_f32", "fa_cast_f32_to_bf16",
     "run_flash_tiled_coarse", "run_flash_tiled_coarse_causal", "attention_forward6", "attention_forward",
     "fa_strerror", "fa_last_cuda_error", "fa_last_impl", "fa_version", "fa_launch_count",
     "fa_watchdog_info",
@@ -59,6 +60,8 @@ def lib() -> ctypes.CDLL:
         L.fa_forward_ex.restype = ctypes.c_int
         L.fa_forward_packed_qkv.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]
         L.fa_forward_packed_qkv.restype = ctypes.c_int
+        L.fa_forward_packed_qkv_ex.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, i32, i32, vp]
+        L.fa_forward_packed_qkv_ex.restype = ctypes.c_int
         L.fa_forward_host.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i32, f32, i32, i32]
         L.fa_forward_host.restype = ctypes.c_int
         L.fa_merge_partials.argtypes = [vp, vp, vp, vp, i64, i32, vp]

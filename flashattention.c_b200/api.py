@@ -54,6 +54,8 @@ def _tma_view(t: torch.Tensor) -> torch.Tensor:
     anything else is made contiguous first."""
     es = t.element_size()
     ok = t.stride(-1) == 1 and t.data_ptr() % 16 == 0 and all((s * es) % 16 == 0 for s in t.stride()[:-1])
+    # a broadcast axis (stride 0, size > 1: K/V expanded over query heads) has no tiled tensor map: materialise it
+    ok = ok and all(s != 0 or n == 1 for s, n in zip(t.stride()[:-1], t.shape[:-1]))
     return t if ok else t.contiguous()
 
 
@@ -65,7 +67,7 @@ def _strides_bhn(t: torch.Tensor):
 
 
 def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False, impl=_lib.FA_IMPL_AUTO, out=None,
-              batch_invariant=False):
+              batch_invariant=False, precise=False):
     """O = softmax(scale * Q K^T [+ causal mask]) V.   scale defaults to 1/sqrt(d).
 
     Q, K, V: CUDA tensors [B*H, N, d] or [B, H, N, d], float32, bfloat16 or float16; strided views with a contiguous last axis
@@ -73,6 +75,8 @@ def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False
     Returns O (same shape/dtype as Q; float32 if out_f32) and, if return_lse, LSE float32 [..., N].
     batch_invariant: FA_FLAG_BATCH_INVARIANT — a (batch, head) slice gives bit-identical results whatever else is in the
     launch (alone, in a larger batch, on another rank of a B x H sharded job); costs the split-KV tail optimisation.
+    precise: FA_FLAG_PRECISE — float32 inputs only: fp32-grade contractions ("3xTF32": hi/lo operand split, three tcgen05 MMAs
+    per contraction) instead of plain tf32; head dims <= 64 on the tensor cores, larger ones on the CUDA-core kernel.
     """
     b, h, nq, nk, d = _shape4(Q, K, V)
     Q, K, V = _tma_view(Q), _tma_view(K), _tma_view(V)
@@ -97,7 +101,7 @@ def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False
         (p.v_stride_b, p.v_stride_h, p.v_stride_n) = _strides_bhn(V)
         p.o_stride_n, p.o_stride_h, p.o_stride_b = d, nq * d, h * nq * d
         p.impl = int(impl)
-        p.flags = _lib.FA_FLAG_BATCH_INVARIANT if batch_invariant else 0
+        p.flags = (_lib.FA_FLAG_BATCH_INVARIANT if batch_invariant else 0) | (_lib.FA_FLAG_PRECISE if precise else 0)
         check(lib().fa_forward_ex(ctypes.byref(p), ctypes.c_void_p(_stream_ptr(Q.device))), "fa_forward_ex")
     return (O, lse) if return_lse else O
 
@@ -117,26 +121,36 @@ def attention_host(q, k, v, causal=False, scale=None, out=None):
     all inside libfa_b200.so (fa_forward_host).  Mirrors what bench_flashattention.py:31-33,70 does around forward()."""
     if q.is_cuda or k.is_cuda or v.is_cuda:
         raise FaError("attention_host takes host tensors")
+    if q.dim() not in (3, 4) or k.dim() != q.dim() or v.dim() != q.dim():
+        raise FaError("expected Q, K, V as [B*H, N, d] or [B, H, N, d]")
+    if not (q.dtype == k.dtype == v.dtype):
+        raise FaError("Q, K, V dtype mismatch")
     if q.dim() == 3:
         b, h, nq, d = 1, q.shape[0], q.shape[1], q.shape[2]
         nk = k.shape[1]
     else:
         b, h, nq, d = q.shape
         nk = k.shape[2]
+    # the library reads and writes raw host pointers: every size it derives from (b, h, nq, nk, d) must be backed by the tensors
+    if tuple(k.shape) != tuple(q.shape[:-2]) + (nk, d) or tuple(v.shape) != tuple(k.shape):
+        raise FaError(f"shape mismatch: Q {tuple(q.shape)} K {tuple(k.shape)} V {tuple(v.shape)}")
     if scale is None:
         scale = 1.0 / math.sqrt(d)
     q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
     o = out if out is not None else torch.empty_like(q)
+    if o.is_cuda or o.shape != q.shape or o.dtype != q.dtype or not o.is_contiguous():
+        raise FaError("out must be a contiguous host tensor of Q's shape and dtype")
     check(lib().fa_forward_host(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), b, h, nq, nk, d, float(scale),
                                 1 if causal else 0, _dtype_code(q)), "fa_forward_host")
     return o
 
 
-def attention_forward6(out, inp, B, T, C, NH, block_size=256, return_lse=False):
+def attention_forward6(out, inp, B, T, C, NH, block_size=256, return_lse=False, precise=True):
     """llm.c-style entry (src/llm.c/attention_forward.cu:1106-1179): inp (B,T,3C) packed QKV fp32 on the device,
     out (B,T,C); causal, scale 1/sqrt(C/NH).  The packed layout is consumed in place through strided TMA maps —
     no permute/unpermute kernels, no temporaries.  `block_size` is accepted and ignored (it only sized the
-    reference's layout kernels)."""
+    reference's layout kernels).  precise=True (the default, like the C symbol): fp32-grade contractions, so the harness's
+    own validate_result(out, 1e-4f) gate (src/llm.c/attention_forward.cu:1262) holds; precise=False: plain tf32."""
     if C % NH:
         raise FaError("C must be divisible by NH")
     hs = C // NH
@@ -146,17 +160,18 @@ def attention_forward6(out, inp, B, T, C, NH, block_size=256, return_lse=False):
         raise FaError("attention_forward: bad tensor sizes")
     with torch.cuda.device(inp.device):
         lse = torch.empty((B, NH, T), dtype=torch.float32, device=inp.device) if return_lse else None
-        check(lib().fa_forward_packed_qkv(inp.data_ptr(), out.data_ptr(), lse.data_ptr() if lse is not None else None, B, T, NH, hs,
-                                          1.0 / math.sqrt(hs), 1, ctypes.c_void_p(_stream_ptr(inp.device))), "fa_forward_packed_qkv")
+        check(lib().fa_forward_packed_qkv_ex(inp.data_ptr(), out.data_ptr(), lse.data_ptr() if lse is not None else None, B, T, NH, hs,
+                                             1.0 / math.sqrt(hs), 1, _lib.FA_FLAG_PRECISE if precise else 0,
+                                             ctypes.c_void_p(_stream_ptr(inp.device))), "fa_forward_packed_qkv_ex")
     return (out, lse) if return_lse else out
 
 
-def attention_forward(kernel_num, out, inp, B, T, C, NH, block_size=256):
+def attention_forward(kernel_num, out, inp, B, T, C, NH, block_size=256, precise=True):
     """Kernel-number dispatch of the llm.c harness (src/llm.c/attention_forward.cu:1183-1211).  Only kernel 6 — the
     reference author's flash kernel — is on the hot path; 1-5 are upstream llm.c comparison kernels (out of scope)."""
     if kernel_num != 6:
         raise FaError("Invalid kernel number (only kernel 6, the flash attention kernel, is provided)")
-    return attention_forward6(out, inp, B, T, C, NH, block_size)
+    return attention_forward6(out, inp, B, T, C, NH, block_size, precise=precise)
 
 
 def merge_partials(o_acc, lse_acc, o_new, lse_new):

@@ -6,6 +6,8 @@ Artefacts
   flashattention.c_b200/libfa_b200.so        C-ABI library (include/fa_b200.h), sm_100a, static cudart
   flashattention.c_b200/flash_b200.so        torch extension `forward(Q,K,V,causal)` (links libfa_b200.so)
   flashattention.c_b200/harness/{fa_check,umma_probe,test}   torch-free harness binaries
+  tests/harness/llmc_main                    the reference's llm.c harness (kernel 6) over the C symbols + oracle CPU loop
+  compat/build/flash/flash.so                compat/src pre-built the way bench_flashattention.py:10 builds it
   oracle/_build/libfa_oracle.so              CPU restatement (checker only)
   oracle/_ref/*                              the reference itself, compiled from /root/reference when present
 """
@@ -63,6 +65,37 @@ def build_harness(force=False):
     return outs
 
 
+def build_test_harness(force=False) -> Path:
+    """tests/harness/llmc_main: the reference's llm.c harness (kernel-6 branch) over the exported C symbols, with the oracle's
+    CPU loop as its checker — test infrastructure, which is why it lives under tests/ and not in the package."""
+    lib = build_lib(force)
+    build_oracle(force, with_ref=False)
+    src = ROOT / "tests" / "harness" / "llmc_main.cu"
+    out = ROOT / "tests" / "harness" / "llmc_main"
+    orc = ROOT / "oracle" / "_build"
+    if force or _stale(out, [src, lib, orc / "libfa_oracle.so"]):
+        _run([NVCC, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-o", out, src, f"-L{PKG}", "-lfa_b200", f"-L{orc}", "-lfa_oracle",
+              "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../flashattention.c_b200", "-Xlinker", "-rpath", "-Xlinker",
+              "$ORIGIN/../../oracle/_build"])
+    return out
+
+
+def build_compat(force=False):
+    """Pre-builds compat/src/{main.cpp,flashattention.cu} exactly as the reference's bench_flashattention.py:10 does
+    (torch.utils.cpp_extension.load, name 'flash', cwd = compat/) into compat/build, so that running the script on the GPU
+    box with TORCH_EXTENSIONS_DIR=compat/build finds an up-to-date build instead of paying the JIT."""
+    compat = ROOT / "compat"
+    so = compat / "build" / "flash" / "flash.so"
+    srcs = [compat / "src" / "main.cpp", compat / "src" / "flashattention.cu", ROOT / "include" / "fa_b200.h"]
+    if not (force or _stale(so, srcs)):
+        return so
+    env = dict(os.environ, TORCH_EXTENSIONS_DIR=str(compat / "build"), TORCH_CUDA_ARCH_LIST="10.0a", MAX_JOBS="4")
+    code = ("from torch.utils.cpp_extension import load; "
+            "load(name='flash', sources=['src/main.cpp', 'src/flashattention.cu'], extra_cuda_cflags=['-O3'], verbose=True)")
+    _run([sys.executable, "-c", code], cwd=str(compat), env=env)
+    return so
+
+
 def build_torch_ext(force=False) -> Path:
     """g++-only build of the pybind module (no device code in it)."""
     import torch
@@ -100,6 +133,9 @@ def build_all(force=False, torch_ext=True, with_ref=True):
     if torch_ext:
         build_torch_ext(force)
     build_oracle(force, with_ref)
+    build_test_harness(force)
+    if torch_ext:
+        build_compat(force)
 
 
 if __name__ == "__main__":

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 #include "fa_fwd_sm100.cuh"
 #include "fa_simt.cuh"
@@ -67,10 +68,16 @@ int current_sm_count() {
 }
 
 // ---- work counters of the persistent kernel: {next item, CTAs finished}; the last CTA of a launch zeroes its pair, so a
-// pair is reusable as soon as the launch that used it has finished.  Launches rotate through a per-device pool so that
-// kernels running concurrently on different streams never share a pair (up to kCounterPool launches in flight).
-constexpr int kCounterPool = 256;
-struct CounterPool { unsigned int* base = nullptr; std::atomic<unsigned int> next{0}; };
+// pair is reusable as soon as the launch that used it has finished.  A pair belongs to ONE (device, stream): launches on a
+// stream run one after the other, so they can share it; launches on different streams may overlap and never do.  A launch
+// that is being captured into a CUDA graph gets no pair at all (static item stride): a graph keeps the pointer for good and
+// may be replayed on any stream, concurrently with eager launches or with another instantiation of itself.
+constexpr int kCounterPool = 1024;   // streams per device that get dynamic scheduling; beyond that: static stride
+struct CounterPool {
+  unsigned int* base = nullptr;
+  int used = 0;
+  std::unordered_map<cudaStream_t, int> slot_of;
+};
 CounterPool g_counters[64];
 std::mutex g_counters_mu;
 
@@ -99,22 +106,29 @@ void install_watchdog_record(int dev) {
   g_wd_installed[dev] = true;
 }
 
-int next_work_counter(unsigned int** out) {
+int next_work_counter(cudaStream_t st, unsigned int** out) {
+  *out = nullptr;
   int dev = 0;
   FA_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return FA_ERR_NO_DEVICE;
   install_watchdog_record(dev);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  FA_CUDA(cudaStreamIsCapturing(st, &cap));
+  if (cap != cudaStreamCaptureStatusNone) return FA_OK;   // captured launch: static stride
+  std::lock_guard<std::mutex> lk(g_counters_mu);
   CounterPool& cp = g_counters[dev];
   if (!cp.base) {
-    std::lock_guard<std::mutex> lk(g_counters_mu);
-    if (!cp.base) {
-      unsigned int* b = nullptr;
-      FA_CUDA(cudaMalloc(&b, kCounterPool * 2 * sizeof(unsigned int)));
-      FA_CUDA(cudaMemset(b, 0, kCounterPool * 2 * sizeof(unsigned int)));   // synchronous w.r.t. the host: done before any launch
-      cp.base = b;
-    }
+    unsigned int* b = nullptr;
+    FA_CUDA(cudaMalloc(&b, kCounterPool * 2 * sizeof(unsigned int)));
+    FA_CUDA(cudaMemset(b, 0, kCounterPool * 2 * sizeof(unsigned int)));   // synchronous w.r.t. the host: done before any launch
+    cp.base = b;
   }
-  *out = cp.base + 2 * (cp.next.fetch_add(1, std::memory_order_relaxed) % kCounterPool);
+  auto it = cp.slot_of.find(st);
+  if (it == cp.slot_of.end()) {
+    if (cp.used == kCounterPool) return FA_OK;   // pool exhausted: this stream runs with the static stride
+    it = cp.slot_of.emplace(st, cp.used++).first;
+  }
+  *out = cp.base + 2 * it->second;
   return FA_OK;
 }
 
@@ -174,9 +188,13 @@ int make_map(CUtensorMap* out, const void* ptr, int elem_size, int elem, int64_t
   if (((sn * elem_size) & 15) || ((sh * elem_size) & 15) || ((sb * elem_size) & 15)) return FA_ERR_ALIGNMENT;
   cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)n, (cuuint64_t)heads, (cuuint64_t)batch};
   cuuint64_t strides[3] = {(cuuint64_t)(sn * elem_size), (cuuint64_t)(sh * elem_size), (cuuint64_t)(sb * elem_size)};
-  // a size-1 axis may come with stride 0; TMA wants a positive multiple of 16
-  for (int i = 0; i < 3; ++i)
-    if (strides[i] == 0) strides[i] = 16;
+  // A size-1 axis may come with stride 0 (its coordinate is always 0, so any stride TMA accepts will do: it wants a positive
+  // multiple of 16).  A broadcast axis (stride 0, size > 1: MQA/GQA-style expanded K/V) cannot be described by a tiled map.
+  for (int i = 0; i < 3; ++i) {
+    if (strides[i] != 0) continue;
+    if (dims[i + 1] != 1) return FA_ERR_UNSUPPORTED;
+    strides[i] = 16;
+  }
   cuuint32_t box[4] = {(cuuint32_t)(128 / elem_size), 128, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(out, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -191,11 +209,11 @@ int make_map(CUtensorMap* out, const void* ptr, int elem_size, int elem, int64_t
   return FA_OK;
 }
 
-template <bool kTF32, int kHeadDim, bool kCausal, bool kOutF32, bool kF16>
+template <bool kTF32, int kHeadDim, bool kCausal, bool kOutF32, bool kF16, bool kPrecise = false>
 int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo, const fa::FwdParams& fp,
               cudaStream_t st) {
-  using T = fa::FwdTraits<kTF32, kHeadDim, kOutF32>;
-  auto kern = fa::fa_fwd_sm100_kernel<kTF32, kHeadDim, kCausal, kOutF32, kF16>;
+  using T = fa::FwdTraits<kTF32, kHeadDim, kOutF32, kPrecise>;
+  auto kern = fa::fa_fwd_sm100_kernel<kTF32, kHeadDim, kCausal, kOutF32, kF16, kPrecise>;
   static bool attr_set[64] = {};  // per kernel instance and per device (the attribute is per device); benign race (idempotent)
   int dev = 0;
   FA_CUDA(cudaGetDevice(&dev));
@@ -225,8 +243,16 @@ int launch_tc_c(bool causal, const CUtensorMap& mq, const CUtensorMap& mk, const
 // rows keep TMA's 16-byte alignment runs on the next instance up: TMA zero-fills the missing columns of Q, K and V in SMEM
 // (zero columns add nothing to q.k, and give zero O columns) and clips them from the O store.
 // 0 = no instance (fp32 d > 128: CUDA-core kernel; FA_B200_NO_WIDE=1 also sends the 512-byte rows there, A/B aid).
+// FA_FLAG_PRECISE (or FA_B200_PRECISE=1 in the environment) on fp32 inputs: the 3xTF32 instance (head dim <= 64), else the
+// fp32 CUDA-core kernel.  16-bit inputs have no precise mode: their operands are exact already.
+bool want_precise(const fa_params* p) {
+  static const bool env = [] { const char* e = getenv("FA_B200_PRECISE"); return e && atoi(e) != 0; }();
+  return p->dtype == FA_F32 && (env || (p->flags & FA_FLAG_PRECISE));
+}
+
 int tc_instance_dim(const fa_params* p) {
   const int d = p->head_dim;
+  if (want_precise(p)) return (d % 4 == 0 && d <= 64) ? 64 : 0;
   static const bool no_wide = [] { const char* e = getenv("FA_B200_NO_WIDE"); return e && atoi(e) != 0; }();
   int di;
   if (p->dtype == FA_F32) di = (d % 4 || d > 128) ? 0 : (d <= 32 ? 32 : (d <= 64 ? 64 : 128));
@@ -246,7 +272,9 @@ int run_tc(const fa_params* p, cudaStream_t st) {
   int rc;
   // fp32 tensors are loaded through TFLOAT32 tensor maps: TMA rounds fp32 -> tf32 to nearest on the way into SMEM, which
   // removes the truncation bias the tensor core would otherwise apply (measured on B200: max error 4.1e-4 -> 9.8e-5 on C1).
-  static const bool tf32_tma = [] { const char* e = getenv("FA_B200_TMA_TF32"); return !(e && atoi(e) == 0); }();
+  static const bool tf32_tma_env = [] { const char* e = getenv("FA_B200_TMA_TF32"); return !(e && atoi(e) == 0); }();
+  const bool precise = want_precise(p);
+  const bool tf32_tma = tf32_tma_env && !precise;   // a precise instance needs the fp32 bits as they are (hi = trunc, lo = rest)
   if ((rc = make_map(&mq, p->q, in_sz, in_dt, p->batch, p->heads, p->n_q, p->head_dim, p->q_stride_b, p->q_stride_h, p->q_stride_n, CU_TENSOR_MAP_SWIZZLE_128B, tf32_tma))) return rc;
   if ((rc = make_map(&mk, p->k, in_sz, in_dt, p->batch, p->heads, p->n_k, p->head_dim, p->k_stride_b, p->k_stride_h, p->k_stride_n, CU_TENSOR_MAP_SWIZZLE_128B, tf32_tma))) return rc;
   // V is the MN-major B operand of P*V: bf16 uses the ordinary 128B swizzle; 32-bit (tf32) MN-major operands must
@@ -274,7 +302,7 @@ int run_tc(const fa_params* p, cudaStream_t st) {
     const int64_t sms = std::max(1, current_sm_count());
     int64_t n_big = (nb / sms) * sms;
     if (2 * (nb - n_big) > sms || getenv("FA_B200_NO_SPLIT_WAVE")) n_big = nb;
-    const bool one_slot = tc_instance_dim(p) * in_sz > 256;   // 512-byte rows: one Q tile per CTA, every item is a 128-row item
+    const bool one_slot = tc_instance_dim(p) * in_sz > 256 || precise;   // 512-byte rows (or 256 + their lo copy): one Q tile per CTA, every item is a 128-row item
     if (one_slot) n_big = 0;
     if (n_big > 0x3fffffff) return FA_ERR_INVALID_ARG;
     fp.n_big = (int)n_big;
@@ -288,7 +316,7 @@ int run_tc(const fa_params* p, cudaStream_t st) {
     const char* ps = getenv("FA_B200_PERSISTENT");
     fp.work_counter = nullptr;
     if (!(ps && atoi(ps) == 0)) {
-      if ((rc = next_work_counter(&fp.work_counter))) return rc;
+      if ((rc = next_work_counter(st, &fp.work_counter))) return rc;
     }
   }
   fp.v_desc_hi = fa::make_sdesc_hi(v_lbo, v_sbo, v_layout);
@@ -322,6 +350,10 @@ int run_tc(const fa_params* p, cudaStream_t st) {
   const bool c = p->causal != 0;
   const int di = tc_instance_dim(p);   // kernel instance (>= head_dim; the tensor maps carry the true head dim)
   const bool f16 = p->dtype == FA_F16;
+  if (precise) {
+    return c ? launch_tc<true, 64, true, false, false, true>(mq, mk, mv, mo, fp, st)
+             : launch_tc<true, 64, false, false, false, true>(mq, mk, mv, mo, fp, st);
+  }
   if (!bf16) {
     if (di == 32) return launch_tc_c<true, 32, false>(c, mq, mk, mv, mo, fp, st);
     if (di == 64) return launch_tc_c<true, 64, false>(c, mq, mk, mv, mo, fp, st);
@@ -387,8 +419,9 @@ struct HostScratch {
   cudaStream_t st_in = nullptr, st_run = nullptr, st_out = nullptr;
   cudaEvent_t ev_in[kHostMaxChunks] = {}, ev_run[kHostMaxChunks] = {};
 };
-HostScratch g_hs;
-std::mutex g_hs_mu;
+// one per device: the buffers, streams and events belong to the device that was current when they were made
+HostScratch g_hs[64];
+std::mutex g_hs_mu[64];
 
 }  // namespace
 
@@ -462,6 +495,11 @@ int fa_forward(const void* q, const void* k, const void* v, void* o, float* lse,
 
 int fa_forward_packed_qkv(const float* inp, float* out, float* lse, int32_t B, int32_t T, int32_t NH, int32_t hs, float scale,
                           int32_t causal, void* stream) {
+  return fa_forward_packed_qkv_ex(inp, out, lse, B, T, NH, hs, scale, causal, 0, stream);
+}
+
+int fa_forward_packed_qkv_ex(const float* inp, float* out, float* lse, int32_t B, int32_t T, int32_t NH, int32_t hs, float scale,
+                             int32_t causal, int32_t flags, void* stream) {
   if (!inp || !out || B <= 0 || T <= 0 || NH <= 0 || hs <= 0) return FA_ERR_INVALID_ARG;
   const int64_t C = (int64_t)NH * hs;
   fa_params p;
@@ -472,6 +510,7 @@ int fa_forward_packed_qkv(const float* inp, float* out, float* lse, int32_t B, i
   p.q_stride_h = p.k_stride_h = p.v_stride_h = hs;
   p.q_stride_b = p.k_stride_b = p.v_stride_b = (int64_t)T * 3 * C;
   p.o_stride_n = C; p.o_stride_h = hs; p.o_stride_b = (int64_t)T * C;
+  p.flags = flags;
   return fa_forward_ex(&p, stream);
 }
 
@@ -480,13 +519,18 @@ int fa_forward_host(const void* qh, const void* kh, const void* vh, void* oh, in
   if (!qh || !kh || !vh || !oh) return FA_ERR_INVALID_ARG;
   if (batch <= 0 || heads <= 0 || n_q <= 0 || n_k <= 0 || head_dim <= 0) return FA_ERR_INVALID_ARG;
   if (dtype != FA_F32 && dtype != FA_BF16 && dtype != FA_F16) return FA_ERR_INVALID_ARG;
+  if (!(scale > 0.f) || !std::isfinite(scale)) return FA_ERR_INVALID_ARG;
   int major = 0;
   int rc = probe_device(&major);
   if (rc) return rc;
+  if (major != 10) return FA_ERR_NO_DEVICE;
   const size_t es = dtype == FA_F32 ? 4 : 2;
   const size_t bq = (size_t)batch * heads * n_q * head_dim * es, bkv = (size_t)batch * heads * n_k * head_dim * es;
-  std::lock_guard<std::mutex> lk(g_hs_mu);
-  HostScratch& s = g_hs;
+  int dev = 0;
+  FA_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return FA_ERR_NO_DEVICE;
+  std::lock_guard<std::mutex> lk(g_hs_mu[dev]);
+  HostScratch& s = g_hs[dev];
   if (!s.st_in) {
     FA_CUDA(cudaStreamCreateWithFlags(&s.st_in, cudaStreamNonBlocking));
     FA_CUDA(cudaStreamCreateWithFlags(&s.st_run, cudaStreamNonBlocking));
@@ -685,7 +729,11 @@ void run_flash_tiled_coarse_causal(float* O, float* K_d, float* Q_d, float* V_d,
 void attention_forward6(float* out, const float* inp, int B, int T, int C, int NH, const int block_size) {
   (void)block_size;  // only sized the reference's permute/unpermute launches, which no longer exist
   const int hs = C / NH;
-  die_on(fa_forward_packed_qkv(inp, out, nullptr, B, T, NH, hs, 1.0f / sqrtf((float)hs), 1, nullptr), "attention_forward6");
+  // the llm.c harness validates `out` against its CPU loop at 1e-4 (src/llm.c/attention_forward.cu:1262): fp32-grade
+  // contractions by default; FA_B200_LLMC_TF32=1 selects the plain tf32 instance (faster, ~3e-4)
+  static const bool fast = [] { const char* e = getenv("FA_B200_LLMC_TF32"); return e && atoi(e) != 0; }();
+  die_on(fa_forward_packed_qkv_ex(inp, out, nullptr, B, T, NH, hs, 1.0f / sqrtf((float)hs), 1, fast ? 0 : FA_FLAG_PRECISE, nullptr),
+         "attention_forward6");
   sync_or_die("attention_forward6");
 }
 void attention_forward(int kernel_num, float* out, float* vaccum, float* qkvr, float* preatt, float* att, const float* inp, int B,

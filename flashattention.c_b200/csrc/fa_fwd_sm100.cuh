@@ -183,42 +183,56 @@ constexpr float kTf32CompEps = 3.5222e-4f;
 constexpr float kTf32CompLog2 = 5.0806e-4f;          // log2(1 + eps), added to the exp2 argument
 constexpr float kTf32CompInv = 1.0f / (1.0f + kTf32CompEps);
 
-template <bool kTF32, int kHeadDim, bool kOutF32>
+// kPrecise (fp32 inputs, head dim <= 64): "3xTF32".  kind::tf32 reads the top 19 bits of an fp32 operand, so a product of two
+// fp32 values loses ~2^-11 per operand.  Every operand x is therefore used twice: as it is (the tensor core sees hi = trunc(x))
+// and as lo = x - trunc(x) (exact in fp32, 11 more bits once truncated), and each contraction runs three MMAs into the same
+// accumulator — hi*hi + lo*hi + hi*lo — which carries ~21 bits per operand, i.e. fp32-grade products.  A tile is then the raw
+// chunks followed by the same number of lo chunks; TMA fills the raw half (plain FLOAT32 maps: no rounding on the way in) and
+// the four warps of slot B — idle in a one-slot instance — write the lo half.  P: hi over S (in place), lo in slot B's S columns.
+template <bool kTF32, int kHeadDim, bool kOutF32, bool kPrecise = false>
 struct FwdTraits {
   static constexpr int kInSize = kTF32 ? 4 : 2;
   static constexpr int kOutSize = (kTF32 || kOutF32) ? 4 : 2;
-  static constexpr int kDChunks = kHeadDim * kInSize / 128;    // boxes per Q/K/V tile
+  static constexpr int kDChunks = kHeadDim * kInSize / 128;    // boxes of Q/K/V data per tile (what TMA loads)
+  static constexpr int kTileChunks = kPrecise ? 2 * kDChunks : kDChunks;   // + the lo copies
   static constexpr int kOChunks = kHeadDim * kOutSize / 128;   // boxes per O tile
   static constexpr int kElemsPerChunk = 128 / kInSize;
   static constexpr int kOutElemsPerChunk = 128 / kOutSize;
-  static constexpr int kTileBytes = kDChunks * kChunkBytes;
-  // Tile slots with their own Q buffer.  512-byte rows (fp32 d = 128, 16-bit d = 256) leave SMEM for one Q tile and a
-  // two-tile K/V ring only: those instances run every item as a 128-row item on slot A (the host never builds 256-row
-  // or split-KV items for them) and slot B's warps idle.  K_(j+1) then streams in under the softmax of step j and
+  static constexpr int kLoadBytes = kDChunks * kChunkBytes;    // bytes TMA delivers per tile
+  static constexpr int kLoOffset = kDChunks * kChunkBytes;     // lo copy of a tile, relative to the tile (kPrecise)
+  static constexpr int kTileBytes = kTileChunks * kChunkBytes;
+  // Tile slots with their own Q buffer.  512-byte rows (fp32 d = 128, 16-bit d = 256, and fp32 d = 64 with its lo copy) leave
+  // SMEM for one Q tile and a two-tile K/V ring only: those instances run every item as a 128-row item on slot A (the host
+  // never builds 256-row or split-KV items for them) and slot B's warps idle.  K_(j+1) then streams in under the softmax of step j and
   // V_(j+1) under Q K^T(j+1) and that softmax — the tensor pipe has nothing else to do for a lone Q tile anyway.
-  static constexpr int kSlots = kDChunks <= 2 ? 2 : 1;
-  static constexpr int kNBuf = kDChunks == 1 ? 8 : (kDChunks == 2 ? 5 : 2);   // K/V ring depth (tiles)
+  static constexpr int kSlots = kTileChunks <= 2 ? 2 : 1;
+  static constexpr int kNBuf = kTileChunks == 1 ? 8 : (kTileChunks == 2 ? 5 : 2);   // K/V ring depth (tiles)
   static constexpr int kUmmaK = 32 / kInSize;                  // K per tcgen05.mma: 8 (tf32) / 16 (bf16)
-  static constexpr int kQSets = kDChunks == 1 ? 2 : 1;         // Q double-buffered across items where SMEM allows
-  static constexpr bool kComp = kTF32 && (FA_OPT_TF32_COMP != 0);   // tf32 truncation compensated instead of reproduced
-  static constexpr bool kPacked = (FA_OPT_F2 != 0) && (!kTF32 || kComp);   // FFMA2 / FADD2 forms in the exp loop
+  static constexpr int kQSets = kTileChunks == 1 ? 2 : 1;      // Q double-buffered across items where SMEM allows
+  static constexpr bool kComp = kTF32 && !kPrecise && (FA_OPT_TF32_COMP != 0);   // tf32 truncation compensated instead of reproduced
+  static constexpr bool kPacked = (FA_OPT_F2 != 0) && (!kTF32 || kComp || kPrecise);   // FFMA2 / FADD2 forms in the exp loop
   static constexpr int kSplitKeys = FA_OPT_SPLIT_KEYS;
   static_assert(kSplitKeys == 64 || kSplitKeys == 96, "P split point");
-  static constexpr int kPolyNum = kDChunks == 1 ? FA_POLY_NUM_NARROW : (kTF32 ? FA_POLY_NUM_TF32 : FA_POLY_NUM_BF16);   // polynomial exp2 on kPolyNum of
-  static constexpr int kPolyDen = kDChunks == 1 ? FA_POLY_DEN_NARROW : (kTF32 ? FA_POLY_DEN_TF32 : FA_POLY_DEN_BF16);   // every kPolyDen element pairs (packed path only)
+  // polynomial exp2 on kPolyNum of every kPolyDen element pairs (packed path only; never in a precise instance: its 7.5e-5
+  // relative error is what that mode exists to avoid)
+  static constexpr int kPolyNum = kPrecise ? 0 : (kDChunks == 1 ? FA_POLY_NUM_NARROW : (kTF32 ? FA_POLY_NUM_TF32 : FA_POLY_NUM_BF16));
+  static constexpr int kPolyDen = kDChunks == 1 ? FA_POLY_DEN_NARROW : (kTF32 ? FA_POLY_DEN_TF32 : FA_POLY_DEN_BF16);
   static constexpr int kSmemData = (kSlots * kQSets + kNBuf) * kTileBytes;
   static constexpr int kNumBarriers = 4 * kQSets /*q full, q free*/ + 2 * kNBuf + 2 /*s_full*/ + 4 /*p_full halves*/ +
-                                      2 /*o_final*/ + 2 /*o_free*/ + 2 * kWorkQueue + 2 /*pv1 done*/;
+                                      2 /*o_final*/ + 2 /*o_free*/ + 2 * kWorkQueue + 2 /*pv1 done*/ +
+                                      (kPrecise ? kNBuf + 2 : 0) /*lo copy of a K/V tile / of the Q tile written*/;
   static constexpr int kSmemBytes = kSmemData + kNumBarriers * 8 + 16 /*tmem ptr*/ + kWorkQueue * 4 + 2 * kBlockM * 4 /*m, l*/ +
                                     1024 /*alignment slack*/;
   static constexpr int kTmemS = 0;        // + 128*t
   static constexpr int kTmemO = 256;      // + kHeadDim*t
+  static constexpr int kTmemPLo = kBlockN;   // kPrecise: lo part of P, in the S columns of the (unused) slot B
   static constexpr int kP1Cols = (kBlockN - kSplitKeys) * kInSize / 4;   // TMEM columns of the second piece of P
   static constexpr int kTmemP1 = 256 + 2 * kHeadDim;                      // + kP1Cols*t (kEarlyS only)
   static constexpr bool kSplitP = (FA_OPT_SPLITP != 0) && (kDChunks > 1 || FA_OPT_SPLITP_NARROW != 0);   // P delivered in two pieces
   static constexpr bool kEarlyHi = (FA_OPT_EARLY_HI != 0) && kSplitP && !kTF32 && (FA_OPT_EARLY_S == 0);
-  static constexpr bool kEarlyS = (FA_OPT_EARLY_S != 0) && kSplitP && (256 + 2 * kHeadDim + 2 * kP1Cols <= 512);
+  static constexpr bool kEarlyS = (FA_OPT_EARLY_S != 0) && !kPrecise && kSplitP && (256 + 2 * kHeadDim + 2 * kP1Cols <= 512);
   static_assert(kDChunks == 1 || kDChunks == 2 || kDChunks == 4, "tile row must be 128, 256 or 512 bytes");
+  static_assert(!kPrecise || (kTF32 && kSlots == 1 && !kOutF32), "precise instances: fp32 operands, one slot (slot B's warps write the lo copies)");
   static_assert(256 + kSlots * kHeadDim <= 512, "TMEM budget");
   static_assert(kSmemBytes <= 227 * 1024, "SMEM budget");
   // SMEM tile index of Q buffer qb = set * 2 + slot (the barrier index): one-slot instances have no tile for slot B
@@ -228,7 +242,7 @@ struct FwdTraits {
 // watchdog tags
 enum : uint32_t {
   TAG_Q_FULL = 1, TAG_KV_FULL = 2, TAG_KV_EMPTY = 3, TAG_S_FULL = 4, TAG_P_FULL = 5, TAG_O_FINAL = 6, TAG_Q_FREE = 7,
-  TAG_O_FREE = 8, TAG_W_FULL = 9, TAG_W_EMPTY = 10, TAG_PV1 = 11
+  TAG_O_FREE = 8, TAG_W_FULL = 9, TAG_W_EMPTY = 10, TAG_PV1 = 11, TAG_CONV = 12
 };
 
 // What one work item is, derived from its index by every warp role on its own.
@@ -284,12 +298,12 @@ FA_DEVINL Item decode_item(const FwdParams& p, int bid) {
 
 // kF16 (16-bit instances only): the operands are IEEE fp16 instead of bf16 — same kind::f16 instruction, operand format 0
 // instead of 1; P <= 2^kRescaleThreshold by construction (lazy rescale), far inside the fp16 range.
-template <bool kTF32, int kHeadDim, bool kCausal, bool kOutF32, bool kF16 = false>
+template <bool kTF32, int kHeadDim, bool kCausal, bool kOutF32, bool kF16 = false, bool kPrecise = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o,
                     const FwdParams p) {
-  using T = FwdTraits<kTF32, kHeadDim, kOutF32>;
+  using T = FwdTraits<kTF32, kHeadDim, kOutF32, kPrecise>;
   constexpr int kQS = T::kQSets;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -307,7 +321,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const uint32_t bar_wfull = bar_ofree + 16;                  // [kWorkQueue]
   const uint32_t bar_wempty = bar_wfull + 8 * kWorkQueue;     // [kWorkQueue]
   const uint32_t bar_pv1 = bar_wempty + 8 * kWorkQueue;       // [2]  second-piece P*V of slot t's latest step has completed
-  const uint32_t s_tmem_ptr = bar_pv1 + 16;                   // 16 bytes
+  const uint32_t bar_conv = bar_pv1 + 16;                     // [kNBuf]  kPrecise: lo copy of the K/V tile in ring slot i written
+  const uint32_t bar_qconv = bar_conv + 8 * T::kNBuf;         // [2]      kPrecise: lo copy of the Q tile written ([1] unused)
+  const uint32_t s_tmem_ptr = kPrecise ? bar_qconv + 16 : bar_pv1 + 16;   // 16 bytes
   const uint32_t s_work = s_tmem_ptr + 16;                    // [kWorkQueue] item indices (-1 = no more work)
   const uint32_t s_ml = s_work + 4 * kWorkQueue;              // m[128], l[128] of slot B (split-KV merge)
 
@@ -339,6 +355,11 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     for (int i = 0; i < kWorkQueue; ++i) {
       mbar_init(bar_wfull + 8 * i, 1);
       mbar_init(bar_wempty + 8 * i, 9);   // MMA warp + 8 softmax warps
+    }
+    if constexpr (kPrecise) {
+      for (int i = 0; i < T::kNBuf; ++i) mbar_init(bar_conv + 8 * i, 4);   // one arrival per warp of slot B
+      mbar_init(bar_qconv, 4);
+      mbar_init(bar_qconv + 8, 4);
     }
     fence_mbar_init();
   }
@@ -402,7 +423,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #if FA_TRACE
           if (seq == 0) FA_TRACE_AT(tm == &tm_k ? 2 : 3, kv_tile, 4);   // ring slot free -> TMA issued (first item: tile == step)
 #endif
-          mbar_arrive_expect_tx(bar_full + 8 * buf, T::kTileBytes);
+          mbar_arrive_expect_tx(bar_full + 8 * buf, T::kLoadBytes);
 #pragma unroll
           for (int c = 0; c < T::kDChunks; ++c)
             tma_load_4d(sKV + buf * T::kTileBytes + c * kChunkBytes, tm, bar_full + 8 * buf, c * T::kElemsPerChunk,
@@ -416,7 +437,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             if (w.n(t) > 0 && !(w.split && t == 1)) {
               const int qb = set * 2 + t;
               if (seq >= kQS) mbar_wait(bar_qfree + 8 * qb, (seq / kQS - 1) & 1, TAG_Q_FREE);
-              mbar_arrive_expect_tx(bar_q + 8 * qb, T::kTileBytes);
+              mbar_arrive_expect_tx(bar_q + 8 * qb, T::kLoadBytes);
 #pragma unroll
               for (int c = 0; c < T::kDChunks; ++c)
                 tma_load_4d(sQ + T::q_tile(qb) * T::kTileBytes + c * kChunkBytes, &tm_q, bar_q + 8 * qb, c * T::kElemsPerChunk,
@@ -491,6 +512,19 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const uint32_t off16 = ((kk >> 2) * kChunkBytes + (kk & 3) * 32) >> 4;
         mma_ss<kTF32>(d, qd + off16, kd + off16, idesc_s, kk > 0 ? 1u : 0u);
       }
+      if constexpr (kPrecise) {   // + lo(Q) K^T + Q lo(K)^T
+        constexpr uint32_t lo16 = T::kLoOffset >> 4;
+        FA_MMA_UNROLL
+        for (int kk = 0; kk < kKStepsS; ++kk) {
+          const uint32_t off16 = ((kk >> 2) * kChunkBytes + (kk & 3) * 32) >> 4;
+          mma_ss<kTF32>(d, qd + lo16 + off16, kd + off16, idesc_s, 1u);
+        }
+        FA_MMA_UNROLL
+        for (int kk = 0; kk < kKStepsS; ++kk) {
+          const uint32_t off16 = ((kk >> 2) * kChunkBytes + (kk & 3) * 32) >> 4;
+          mma_ss<kTF32>(d, qd + off16, kd + lo16 + off16, idesc_s, 1u);
+        }
+      }
     };
     // one 64-key half of S_t = Q_t K^T: keys [64*half, 64*half + 64) of the tile -> S columns [64*half, +64) (kEarlyHi).
     // K is K-major: key row r of a 128-byte column chunk sits at r * 128 bytes (swizzled inside 1024-byte groups of 8 rows)
@@ -517,6 +551,16 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mma_ts<kTF32>(d, a + ks * 8, vd + static_cast<uint32_t>(ks * (T::kUmmaK * 128 / 16)), idesc_pv,
                       (accumulate || ks > 0) ? 1u : 0u);
       }
+      if constexpr (kPrecise) {   // + lo(P) V + P lo(V)
+        constexpr uint32_t lo16 = T::kLoOffset >> 4;
+        const uint32_t a_lo = tmem_base + T::kTmemS + T::kTmemPLo;
+        FA_MMA_UNROLL
+        for (int ks = ks0; ks < ks1; ++ks)
+          mma_ts<kTF32>(d, a_lo + ks * 8, vd + static_cast<uint32_t>(ks * (T::kUmmaK * 128 / 16)), idesc_pv, 1u);
+        FA_MMA_UNROLL
+        for (int ks = ks0; ks < ks1; ++ks)
+          mma_ts<kTF32>(d, a + ks * 8, vd + lo16 + static_cast<uint32_t>(ks * (T::kUmmaK * 128 / 16)), idesc_pv, 1u);
+      }
     };
     int ring = 0;                 // K/V ring index, same sequence as the producer's
     uint32_t p_par = 0;           // bit t: parity of the next bar_p[t] phase (one phase per K/V step of slot t, over all items)
@@ -539,7 +583,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #if FA_TRACE
     int steps_a = 0, steps_b = 0;
 #endif
-    auto wait_full = [&](int i) { mbar_wait(bar_full + 8 * (i % T::kNBuf), (i / T::kNBuf) & 1, TAG_KV_FULL); };
+    // a K/V tile is usable once TMA has delivered it — in a precise instance, once its lo copy has been written next to it
+    auto wait_full = [&](int i) {
+      mbar_wait((kPrecise ? bar_conv : bar_full) + 8 * (i % T::kNBuf), (i / T::kNBuf) & 1, kPrecise ? TAG_CONV : TAG_KV_FULL);
+    };
     // P_t(j) V -> O_t in two 64-key halves as the softmax warps deliver them, then (unless this was the slot's last
     // K/V tile of the item) S_t(j+1); the tensor pipe executes in issue order, so S_t(j+1) may overwrite the columns
     // P_t(j) aliased.
@@ -617,7 +664,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       for (int t = 0; t < 2; ++t) {
         if (w.n(t) > 0 && !(w.split && t == 1)) {
           const int qb = set * 2 + t;
-          mbar_wait(bar_q + 8 * qb, (q_par >> qb) & 1u, TAG_Q_FULL);
+          mbar_wait((kPrecise ? bar_qconv : bar_q) + 8 * qb, (q_par >> qb) & 1u, kPrecise ? TAG_CONV : TAG_Q_FULL);
           q_par ^= 1u << qb;
         }
       }
@@ -713,6 +760,54 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       // who will read TMEM in this item's epilogue: both slots of a 256-row item that had work; slot A alone (its own
       // accumulator and, for the merge, slot B's) in a 128-row item
       of_pend = w.single ? 1u : ((w.n0 > 0 ? 1u : 0u) | (w.n1 > 0 ? 2u : 0u));
+    }
+  } else if (kPrecise && warp >= 4) {
+    // =========================== lo copies (precise instances: the warps of slot B) ===========================
+    // lo = x - trunc_tf32(x) over the raw chunks of a tile, element by element: the lo chunks use the same swizzle as the raw
+    // ones, so the copy is layout-agnostic.  Tiles are taken in the producer's order (first kNBuf K/V tiles, Q, the rest).
+    const int ct = static_cast<int>(threadIdx.x) - 4 * 32;
+    auto write_lo = [&](uint32_t tile, uint32_t bar) {
+#pragma unroll 4
+      for (int i = ct; i < T::kLoadBytes / 16; i += 128) {
+        uint32_t x[4];
+        ld_shared_v4(tile + i * 16, x[0], x[1], x[2], x[3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          x[e] = __float_as_uint(__uint_as_float(x[e]) - __uint_as_float(x[e] & 0xFFFFE000u));
+        st_shared_v4(tile + T::kLoOffset + i * 16, x[0], x[1], x[2], x[3]);
+      }
+      fence_proxy_async_smem();   // generic-proxy writes -> visible to tcgen05.mma's operand reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    int ring = 0;
+    uint32_t q_par = 0;
+    for (int seq = 0;; ++seq) {
+      const int item = next_item(seq);
+      if (item < 0) break;
+      const Item w = decode_item<kCausal>(p, item);
+      if (w.n_max == 0) continue;
+      const int qb = (seq % kQS) * 2;
+      auto conv_q = [&]() {
+        mbar_wait(bar_q + 8 * qb, q_par & 1u, TAG_Q_FULL);
+        q_par ^= 1u;
+        write_lo(sQ + T::q_tile(qb) * T::kTileBytes, bar_qconv + 8 * qb);
+      };
+      bool q_done = false;
+      if (seq == 0) {
+        conv_q();
+        q_done = true;
+      }
+      for (int i = 0; i < 2 * w.n_max; ++i, ++ring) {
+        if (!q_done && i == T::kNBuf) {
+          conv_q();
+          q_done = true;
+        }
+        const int buf = ring % T::kNBuf;
+        mbar_wait(bar_full + 8 * buf, (ring / T::kNBuf) & 1, TAG_KV_FULL);
+        write_lo(sKV + buf * T::kTileBytes, bar_conv + 8 * buf);
+      }
+      if (!q_done) conv_q();
     }
   } else {
     // =========================== softmax + epilogue (warps 0-7) ===========================
@@ -897,6 +992,18 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             }
             if constexpr (kTF32) {
               tmem_st32(own ? tP1 + (cc - kChunks0) * 32 : tS + cc * 32, reinterpret_cast<uint32_t*>(&s[cc * 32]));
+              if constexpr (kPrecise) {   // what kind::tf32 drops from P goes to the lo columns
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                  uint32_t lo[16];
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const float x = s[cc * 32 + h2 * 16 + i];
+                    lo[i] = __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
+                  }
+                  tmem_st16(tS + T::kTmemPLo + cc * 32 + h2 * 16, lo);
+                }
+              }
             } else {
               uint32_t pk[16];
 #pragma unroll
@@ -932,14 +1039,17 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tc_fence_after();
       if (tracer && seq == 0) FA_TRACE_MISC(t, 3);
       // scale of this slot's accumulator and of the partner's partial (split-KV tail items only) in the final O
-      float f_self = (n_mine > 0 && l > 0.f) ? 1.0f / l : 0.f;
+      // A row that has seen no visible key (m still -inf: causal with n_q > n_k masks whole rows inside partly visible
+      // tiles) is O = 0, LSE = -inf like the oracle's; its l may hold 2^-126 crumbs from the polynomial exp2 route, which
+      // clamps its argument, so the test is on m, not on l alone.
+      const bool seen = n_mine > 0 && m != -INFINITY && l > 0.f;
+      float f_self = seen ? 1.0f / l : 0.f;
       float f_other = 0.f;
-      float lse_val = -INFINITY;
-      {
-        const float m_safe = (m == -INFINITY) ? 0.f : m;
-        if (n_mine > 0 && l > 0.f) lse_val = m_safe * p.scale + logf(l);
-      }
-      const bool stores = !(w.single && t == 1);        // slot B of a 128-row item owns no output rows
+      float lse_val = seen ? m * p.scale + logf(l) : -INFINITY;
+      // slot B of a 128-row item owns no output rows; neither does a slot whose 128 rows all lie past n_q (slot B of the
+      // last 256-row block when n_q % 256 is in [1, 128], the dead second item of a one-slot instance): the TMA store
+      // would clip every row, so nothing is staged or stored
+      const bool stores = !(w.single && t == 1) && (w.row0 + t * kBlockM) < p.n_q;
       const bool merge = w.split && w.n1 > 0;
       if (merge) {
         if (t == 1) {
@@ -969,9 +1079,15 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       constexpr int kColsPerChunk = T::kOutElemsPerChunk;  // 32 (fp32) or 64 (bf16)
       constexpr int kLastCol0 = (kRounds * T::kDChunks - 1) * kColsPerChunk + (kColsPerChunk / 32 - 1) * 32;
       if (!stores) {
-        // slot B of a 128-row item: nothing to read from TMEM (slot A merges O_B) and no output rows; its Q buffer was unused
+        // nothing to read from TMEM (slot A merges O_B) and no output rows; the slot's Q buffer was unused
         if ((warp & 3) == 0 && lane == 0) mbar_arrive(bar_qfree + 8 * (set * 2 + t));
       } else {
+        if (n_mine == 0) {
+          // Rows without a single K/V tile (causal, n_q > n_k) are written as zeros from the staging buffer.  A slot with work
+          // is ordered after the previous store out of this buffer by bar_qfree -> Q load -> bar_s; this path has no such
+          // chain, so order every thread of the slot behind the store thread, which has waited for that store to be read.
+          named_bar_sync(1 + t, 128);
+        }
 #pragma unroll
         for (int round = 0; round < kRounds; ++round) {
 #pragma unroll

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define FA_B200_VERSION 100 /* major*100 + minor */
+#define FA_B200_VERSION 101 /* major*100 + minor */
 
 /* element type of Q, K, V (and of O unless stated otherwise) */
 enum fa_dtype {
@@ -52,7 +52,15 @@ enum fa_flags {
    * (batch, head) slice gives bit-identical results alone, inside a larger batch, or on another rank of a B x H
    * sharded job.  Off by default: the scheduler then splits the K/V range of the last partial wave's tiles over two
    * tile slots (split-KV with a log-sum-exp merge), which is faster for small grids but rounds differently. */
-  FA_FLAG_BATCH_INVARIANT = 1
+  FA_FLAG_BATCH_INVARIANT = 1,
+  /* fp32 inputs only: fp32-grade contractions instead of plain tf32 ("3xTF32").  Every operand x is fed to the tensor core
+   * twice — as it is (kind::tf32 reads hi = the top 19 bits) and as lo = x - hi — and both contractions run hi*hi + lo*hi +
+   * hi*lo into one fp32 accumulator; exp2 is MUFU only (no polynomial).  Head dims <= 64 run on the tcgen05 kernel (about
+   * 3x the tensor work of the default), larger ones on the fp32 CUDA-core kernel.  This is what lets the llm.c harness
+   * keep its validate_result(out, 1e-4f) gate (src/llm.c/attention_forward.cu:1262), which plain tf32 (10-bit mantissa:
+   * an output row that copies one V row is already off by up to 2.4e-4) cannot meet; the attention_forward[6] shims set
+   * it.  FA_B200_PRECISE=1 in the environment sets it for every fp32 call of the process. */
+  FA_FLAG_PRECISE = 2
 };
 
 /* strided problem description.  Strides are in ELEMENTS; the head_dim axis is contiguous. */
@@ -99,6 +107,10 @@ int fa_forward_ex(const fa_params* p, void* stream);
 int fa_forward_packed_qkv(const float* inp, float* out, float* lse,
                           int32_t B, int32_t T, int32_t NH, int32_t hs,
                           float scale, int32_t causal, void* stream);
+/* the same with a bit set of enum fa_flags (FA_FLAG_PRECISE is what the attention_forward[6] shims pass) */
+int fa_forward_packed_qkv_ex(const float* inp, float* out, float* lse,
+                             int32_t B, int32_t T, int32_t NH, int32_t hs,
+                             float scale, int32_t causal, int32_t flags, void* stream);
 
 /*
  * fa_forward_host — the same operator with HOST buffers: copies Q, K, V to the device, runs

@@ -82,7 +82,7 @@ def test_tma_view_passes_aligned_strided_views_and_copies_the_rest():
 
 def test_version_and_strerror(fab):
     L = fab.lib()
-    assert L.fa_version() == 100
+    assert L.fa_version() == 101
     assert L.fa_strerror(0) == b"ok"
     assert b"no CPU fallback" in L.fa_strerror(-2)
     assert L.fa_strerror(-12345) == b"unknown status"
