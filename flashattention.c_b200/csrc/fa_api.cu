@@ -296,6 +296,9 @@ int run_tc(const fa_params* p, cudaStream_t st) {
   fp.causal_offset = (int)(p->n_k - p->n_q);
   fp.num_m_blocks = (int)((p->n_q + 2 * fa::kBlockM - 1) / (2 * fa::kBlockM));
   fp.lse = p->lse;
+  fp.o_ptr = p->o;
+  fp.o_sb = p->o_stride_b; fp.o_sh = p->o_stride_h; fp.o_sn = p->o_stride_n;
+  fp.o_row_bytes = p->head_dim * out_sz;
   {
     // whole waves of 256-row CTAs; a remainder of at most SMs/2 blocks runs as twice as many 128-row CTAs (one wave)
     const int64_t nb = (int64_t)fp.num_m_blocks * fp.heads * fp.batch;

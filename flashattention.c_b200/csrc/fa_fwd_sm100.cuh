@@ -167,6 +167,9 @@ struct FwdParams {
                       // 0: it runs slot A only
   int n_items;        // n_big + 2 * (number of 256-row blocks run as pairs of 128-row items)
   unsigned int* work_counter;   // [0] next item, [1] CTAs finished (the last one resets both); nullptr: static stride
+  void* o_ptr;        // O in global memory with its element strides: only for rows that see no key (zeros, no staging buffer)
+  int64_t o_sb, o_sh, o_sn;
+  int o_row_bytes;    // head_dim * sizeof(output element), a multiple of 16
 };
 constexpr int kTraceSteps = 48;
 
@@ -254,6 +257,10 @@ struct Item {
   int kv_first1;           // first K/V tile of slot B (split mode), else 0
   int n_max;
   FA_DEVINL int n(int t) const { return t == 0 ? n0 : n1; }
+  // Slot t gets a Q tile of its own in this item (in split mode slot B reads slot A's).  The ownership protocol of a Q buffer
+  // (bar_q: tile landed; bar_qfree: the O tile staged there has been read out by its TMA store) has exactly one phase per
+  // item for which this holds, on the producer's, the MMA warp's and the epilogue's side alike.
+  FA_DEVINL bool loads_q(int t) const { return n(t) > 0 && !(split && t == 1); }
 };
 template <bool kCausal>
 FA_DEVINL Item decode_item(const FwdParams& p, int bid) {
@@ -397,6 +404,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     // =========================== item fetch + TMA producer ===========================
     if (lane == 0) {
       int ring = 0;   // running index into the K/V ring; the MMA issuer consumes tiles in exactly this order
+      uint32_t qf_used = 0, qf_par = 0;   // per Q buffer: a tile has been loaded before / parity of the next bar_qfree phase
       for (int seq = 0;; ++seq) {
         // the first item of a CTA is its block index (no round trip to the counter on the critical start-up path, and
         // no queue: every role knows it); later items come from the counter, or from a static stride without one
@@ -434,9 +442,16 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         auto load_q = [&]() {
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            if (w.n(t) > 0 && !(w.split && t == 1)) {
+            if (w.loads_q(t)) {
               const int qb = set * 2 + t;
-              if (seq >= kQS) mbar_wait(bar_qfree + 8 * qb, (seq / kQS - 1) & 1, TAG_Q_FREE);
+              // the previous tile in this buffer (if any) must have left as an O tile: one bar_qfree phase per load, counted
+              // here and not derived from the item number — items and slots without a Q tile have no phase (a barrier that
+              // runs a phase ahead of or behind its waiter makes the parity test alias)
+              if (qf_used & (1u << qb)) {
+                mbar_wait(bar_qfree + 8 * qb, (qf_par >> qb) & 1u, TAG_Q_FREE);
+                qf_par ^= 1u << qb;
+              }
+              qf_used |= 1u << qb;
               mbar_arrive_expect_tx(bar_q + 8 * qb, T::kLoadBytes);
 #pragma unroll
               for (int c = 0; c < T::kDChunks; ++c)
@@ -662,7 +677,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       // Q tiles of this item
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        if (w.n(t) > 0 && !(w.split && t == 1)) {
+        if (w.loads_q(t)) {
           const int qb = set * 2 + t;
           mbar_wait((kPrecise ? bar_qconv : bar_q) + 8 * qb, (q_par >> qb) & 1u, kPrecise ? TAG_CONV : TAG_Q_FULL);
           q_par ^= 1u << qb;
@@ -1046,10 +1061,14 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       float f_self = seen ? 1.0f / l : 0.f;
       float f_other = 0.f;
       float lse_val = seen ? m * p.scale + logf(l) : -INFINITY;
-      // slot B of a 128-row item owns no output rows; neither does a slot whose 128 rows all lie past n_q (slot B of the
-      // last 256-row block when n_q % 256 is in [1, 128], the dead second item of a one-slot instance): the TMA store
-      // would clip every row, so nothing is staged or stored
-      const bool stores = !(w.single && t == 1) && (w.row0 + t * kBlockM) < p.n_q;
+      // Who writes output rows.  A slot that got a Q tile (=> it has keys, and rows below n_q) stages its O tile in that
+      // buffer, stores it with TMA and then releases the buffer to the producer.  A slot without one has no staging buffer
+      // either — its Q buffer may already be receiving the next item's tile — so rows that exist but see no key at all
+      // (causal, n_q > n_k) are written as zeros with plain global stores, and slots without rows (slot B of a 128-row item;
+      // rows past n_q: slot B of the last 256-row block when n_q % 256 is in [1, 128], the dead second item of a one-slot
+      // instance) write nothing.
+      const bool stores = w.loads_q(t);
+      const bool zero_rows = !stores && !(w.single && t == 1) && q_row < p.n_q;
       const bool merge = w.split && w.n1 > 0;
       if (merge) {
         if (t == 1) {
@@ -1079,15 +1098,13 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       constexpr int kColsPerChunk = T::kOutElemsPerChunk;  // 32 (fp32) or 64 (bf16)
       constexpr int kLastCol0 = (kRounds * T::kDChunks - 1) * kColsPerChunk + (kColsPerChunk / 32 - 1) * 32;
       if (!stores) {
-        // nothing to read from TMEM (slot A merges O_B) and no output rows; the slot's Q buffer was unused
-        if ((warp & 3) == 0 && lane == 0) mbar_arrive(bar_qfree + 8 * (set * 2 + t));
-      } else {
-        if (n_mine == 0) {
-          // Rows without a single K/V tile (causal, n_q > n_k) are written as zeros from the staging buffer.  A slot with work
-          // is ordered after the previous store out of this buffer by bar_qfree -> Q load -> bar_s; this path has no such
-          // chain, so order every thread of the slot behind the store thread, which has waited for that store to be read.
-          named_bar_sync(1 + t, 128);
+        if (zero_rows) {
+          uint8_t* row = static_cast<uint8_t*>(p.o_ptr) +
+                         (static_cast<int64_t>(w.batch) * p.o_sb + static_cast<int64_t>(w.head) * p.o_sh + static_cast<int64_t>(q_row) * p.o_sn) * T::kOutSize;
+          for (int b = 0; b < p.o_row_bytes; b += 16) *reinterpret_cast<uint4*>(row + b) = make_uint4(0u, 0u, 0u, 0u);
+          if (p.lse != nullptr) p.lse[(static_cast<int64_t>(w.batch) * p.heads + w.head) * p.n_q + q_row] = -INFINITY;
         }
+      } else {
 #pragma unroll
         for (int round = 0; round < kRounds; ++round) {
 #pragma unroll
