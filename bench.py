@@ -10,6 +10,14 @@ data-path collective and per-GPU work is fixed ("weak"): every rank runs the sam
 
 --workload C5 is the ring-attention config (B=1 H=32 d=128 N=131072 bf16, sequence split over the ranks, strong scaling).
 
+With N > 1 the same JSON line also carries the multi-GPU workloads BASELINE.json names, each with a `parity` field:
+  c4_sharded / c3_sharded   configs 4 / 3 at their GLOBAL size (B*H = 128 heads) split over the N ranks, no collective (strong
+             scaling): ms (max over ranks), total TFLOP/s, the same problem on one GPU in the same run, efficiency t1/(N*tN);
+             parity = every rank's shard bit-equal to the unsharded forward (FA_FLAG_BATCH_INVARIANT) + sampled rows vs fp64
+  c5_ring    config 5 (N=131072 split over the ranks): ms, total and per-GPU TFLOP/s, fraction of the sustained bf16 peak,
+             overlap (same kernels without transfers / ring), the NCCL transport beside the p2p one; parity = the ring's
+             shard vs ONE single-GPU kernel over the full sequence + sampled rows vs fp64
+
 Prints ONE JSON line on rank 0:
   value      TFLOP/s, whole job, kernel timed with CUDA events on the launch stream, inputs resident in HBM,
              L2 flushed (256 MiB write) before every timed step
@@ -42,6 +50,7 @@ WORKLOADS = {  # name: (B, H, N, d, dtype)
     "C4": (4, 32, 8192, 128, "bf16"),
 }
 L2_FLUSH_BYTES = 256 << 20
+HOST_BINDING = {"policy": "unset"}     # filled by main(): how this rank was bound to cores / a NUMA node
 
 
 def flops_of(B, H, N, d):
@@ -59,6 +68,97 @@ def load_peaks():
         return {"bf16": float(j["bf16_tflops"]), "bf16_sustained": float(j.get("bf16_tflops_sustained", j["bf16_tflops"])),
                 "hbm": float(j["hbm_gbs"]), "src": "MEASURED_PEAKS.json"}
     return {"bf16": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+def pin_to_gpu_numa(local_rank, world):
+    """Bind this process (and so the pinned host buffers it allocates afterwards: first-touch) to a private slice of the
+    cores of a NUMA node.  FA_BENCH_NUMA=local (default): the node the GPU hangs off (sysfs numa_node of its PCI function);
+    spread: nodes round-robin over the local ranks, so that N ranks' host copies do not all pull from one node's DRAM;
+    off: leave the affinity alone.  Returns a description for the JSON line."""
+    policy = os.environ.get("FA_BENCH_NUMA", "local")
+    info = {"policy": policy}
+    if policy == "off" or not hasattr(os, "sched_setaffinity"):
+        return info
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        nodes = {}
+        for d_ in sorted(Path("/sys/devices/system/node").glob("node[0-9]*")):
+            cpus = []
+            for part in (d_ / "cpulist").read_text().strip().split(","):
+                if part:
+                    a, _, b = part.partition("-")
+                    cpus += list(range(int(a), int(b or a) + 1))
+            if cpus:
+                nodes[int(d_.name[4:])] = cpus
+        allowed = set(os.sched_getaffinity(0))
+        nodes = {n: [c for c in cs if c in allowed] for n, cs in nodes.items()}
+        nodes = {n: cs for n, cs in nodes.items() if cs}
+        if not nodes:
+            return info
+
+        def gpu_node(i):
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(i)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            f = Path("/sys/bus/pci/devices") / bus.lower()[-12:] / "numa_node"
+            n = int(f.read_text()) if f.exists() else -1
+            return n if n in nodes else sorted(nodes)[0]
+
+        order = sorted(nodes)
+        node_of = [order[i % len(order)] if policy == "spread" else gpu_node(i) for i in range(world)]
+        mine = node_of[local_rank]
+        peers = [i for i in range(world) if node_of[i] == mine]
+        cpus = nodes[mine]
+        per = max(1, len(cpus) // len(peers))
+        k = peers.index(local_rank)
+        sl = cpus[k * per:(k + 1) * per] or cpus
+        os.sched_setaffinity(0, sl)
+        info.update({"numa_node": mine, "gpu_numa_node": gpu_node(local_rank), "cpus": f"{sl[0]}-{sl[-1]}", "n_cpus": len(sl),
+                     "numa_nodes": len(nodes)})
+    except Exception as e:  # affinity is an optimisation: never fail the bench over it
+        info["error"] = repr(e)[:120]
+    return info
+
+
+def copy_floor_ms(torch, hosts, o_host, devs, reps=5):
+    """Raw pinned-host <-> device copies of exactly the e2e step's bytes (Q, K, V in on one stream, O out on another, in
+    parallel): the host/PCIe ceiling under which no e2e time can go.  Caller brackets it with barriers so that all ranks copy
+    at the same time."""
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    o_dev = torch.empty_like(devs[0])
+    best = None
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_in):
+            for h, d_ in zip(hosts, devs):
+                d_.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            o_host.copy_(o_dev, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        best = dt if best is None else min(best, dt)
+    return best
+
+
+def fp64_rows_check(torch, q, k, v, o, lse, scale, rows, seed):
+    """Checker (torch fp64 on the GPU, not the product): `rows` sampled query rows of every (batch, head) of q [B,H,n_q,d]
+    against ALL keys of k, v [B,H,n_k,d]; returns (max |O - ref|, max |LSE - ref|)."""
+    B, H, n_q, d = q.shape
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    idx = torch.randperm(n_q, generator=g)[:rows].sort().values.to(q.device)
+    err_o = err_l = 0.0
+    for h0 in range(0, H, 4):
+        qs = q[:, h0:h0 + 4, idx].double()
+        s = (qs @ k[:, h0:h0 + 4].double().transpose(-1, -2)) * scale
+        ref_l = torch.logsumexp(s, dim=-1)
+        ref_o = torch.softmax(s, dim=-1) @ v[:, h0:h0 + 4].double()
+        err_o = max(err_o, float((o[:, h0:h0 + 4, idx].double() - ref_o).abs().max()))
+        if lse is not None:
+            err_l = max(err_l, float((lse[:, h0:h0 + 4, idx].double() - ref_l).abs().max()))
+        del qs, s, ref_l, ref_o
+    return err_o, err_l
 
 
 class ClockSampler(threading.Thread):
@@ -229,11 +329,18 @@ def run_ours(args, torch, dist, rank, world, device):
         fab.attention_host(hosts[0], hosts[1], hosts[2], causal=False, scale=scale, out=o_host)
     e2e_s = time.perf_counter() - t0
 
+    # the host/PCIe ceiling for the same bytes, all ranks copying at once (explains what is left of e2e at N > 1)
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=device)
+        dist.barrier()
+    floor_ms = copy_floor_ms(torch, hosts, o_host, devs)
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s, floor_ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s = t.tolist()
+        total_ms, e2e_s, floor_ms = t.tolist()
+    want_multi = world > 1 and not args.no_extra
     if rank != 0:
+        if want_multi:
+            guarded_multi(None, args, torch, dist, fab, rank, world, device, flush)
         return None
     fl = flops_of(B, H, N, d)
     ms_per_step = total_ms / args.steps
@@ -252,11 +359,17 @@ def run_ours(args, torch, dist, rank, world, device):
                    "flops_per_step_per_gpu": fl, "algorithmic_bytes_per_step_per_gpu": bytes_of(B, H, N, d, es)},
         "e2e": {"value": round(fl * world / (e2e_s / e2e_steps) * 1e-12, 3), "unit": "TFLOP/s", "ms_per_step": round(e2e_s / e2e_steps * 1e3, 4),
                 "h2d_bytes_per_step": 3 * q.numel() * es, "d2h_bytes_per_step": q.numel() * es, "steps": e2e_steps,
-                "api": "fa_forward_host (C-ABI, pinned host buffers)"},
+                "api": "fa_forward_host (C-ABI, pinned host buffers)",
+                "host_copy_floor_ms": round(floor_ms, 4),
+                "host_copy_floor_note": "raw pinned-host<->device copies of the same bytes, no kernel, all ranks at once, max over ranks: "
+                                        "what the host memory / PCIe path allows at this N; e2e minus this is the operator's own cost",
+                "host_binding": HOST_BINDING},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "achieved": round(achieved, 2), "peak": round(peak, 1), "unit": "TFLOP/s",
                      "frac": round(achieved / peak, 4), "traffic": TRAFFIC_BYTES.get(args.workload),
+                     "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full "
+                                       "capture (profiles/r02_ncu_summary.md), not re-measured in this run",
                      "peak_source": peaks["src"] + (" bf16_tflops / 2 (tf32, derived)" if dtype == "f32" else " bf16_tflops (burst)"),
                      "kernel": "fa_fwd_sm100_kernel", "hbm_gbs_achieved": round(bytes_of(B, H, N, d, es) / (ms_per_step * 1e-3) * 1e-9, 1)},
         "ms_min": round(min(ms), 5), "ms_median": round(sorted(ms)[len(ms) // 2], 5), "wall_s": round(wall, 3),
@@ -266,6 +379,8 @@ def run_ours(args, torch, dist, rank, world, device):
         line["cpu_baseline"]["reference_cpu_loop"] = reference_cpu_loop(5.0)   # the reference's own scalar CPU loop, beside it
     if world == 1 and not args.no_extra:
         line["other_configs"] = other_configs(torch, fab, device, flush, peaks)
+    if want_multi:
+        line.update(guarded_multi(line, args, torch, dist, fab, rank, world, device, flush))
     return line
 
 
@@ -289,7 +404,170 @@ def other_configs(torch, fab, device, flush, peaks):
                      "frac_tensor_peak": round(flops_of(B, H, N, d) / med * 1e-9 / peak, 4),
                      "hbm_gbs": round(bytes_of(B, H, N, d, es) / med * 1e-6, 1), "frac_hbm_peak": round(bytes_of(B, H, N, d, es) / med * 1e-6 / peaks["hbm"], 4)}
         del q, k, v, out
+    # FA_FLAG_PRECISE (3xTF32) beside the default tf32 instance on the headline shape, and the llm.c harness shape through the
+    # packed-QKV entry (what the exported attention_forward symbol runs: precise by default, tf32 on request)
+    B, H, N, d, _ = WORKLOADS["C2"]
+    _, (q, k, v) = make_inputs(torch, B, H, N, d, "f32", device, 99)
+    out = torch.empty_like(q)
+    ms = sorted(time_kernel(torch, lambda: fab.attention(q, k, v, scale=1.0 / math.sqrt(d), out=out, precise=True), 10, 3, flush))[5]
+    res["C2_precise_3xtf32"] = {"ms": round(ms, 5), "tflops_algorithmic": round(flops_of(B, H, N, d) / ms * 1e-9, 1),
+                                "note": "three tcgen05 MMAs per contraction: the tensor pipe does 3x these FLOPs"}
+    del q, k, v, out
+    Bl, Tl, Cl, NHl = 6, 4096, 768, 12
+    inp = torch.rand(Bl, Tl, 3 * Cl, device=device) * 2 - 1
+    outl = torch.empty(Bl, Tl, Cl, device=device)
+    fl_l = 4.0 * Bl * NHl * (Cl // NHl) * Tl * (Tl + 1) / 2
+    for label, prec in (("llmc_B6_T4096_precise", True), ("llmc_B6_T4096_tf32", False)):
+        ms = sorted(time_kernel(torch, lambda: fab.attention_forward(6, outl, inp, Bl, Tl, Cl, NHl, 256, precise=prec), 10, 3, flush))[5]
+        res[label] = {"ms": round(ms, 5), "tflops_causal": round(fl_l / ms * 1e-9, 1)}
+    del inp, outl
+    # config 5 on ONE GPU: the whole 131072-long sequence in one launch (the ring's single-GPU baseline)
+    Hh, Nn, dd = 32, 131072, 128
+    g = torch.Generator(device=device).manual_seed(5)
+    q, k, v = (torch.randn(1, Hh, Nn, dd, device=device, generator=g).to(torch.bfloat16) for _ in range(3))
+    out = torch.empty_like(q)
+    ms = min(time_kernel(torch, lambda: fab.attention(q, k, v, out=out), 2, 1, flush))
+    res["C5_one_gpu"] = {"ms": round(ms, 3), "tflops": round(flops_of(1, Hh, Nn, dd) / ms * 1e-9, 1),
+                         "frac_tensor_peak_sustained": round(flops_of(1, Hh, Nn, dd) / ms * 1e-9 / peaks["bf16_sustained"], 4)}
+    del q, k, v, out
     return res
+
+
+def guarded_multi(line, args, torch, dist, fab, rank, world, device, flush, limit_s=420.0):
+    """multi_gpu_sections under a deadline: if a rank dies or a collective hangs there, rank 0 still prints the headline line
+    (already complete at this point) with the failure noted, and every rank exits instead of waiting for the NCCL timeout."""
+    def bail():
+        if line is not None:
+            print(json.dumps({**line, "multi_gpu_error": f"multi-GPU sections did not finish within {limit_s:.0f} s"}), flush=True)
+        os._exit(0)
+
+    timer = threading.Timer(limit_s, bail)
+    timer.daemon = True
+    timer.start()
+    try:
+        return multi_gpu_sections(args, torch, dist, fab, rank, world, device, flush)
+    finally:
+        timer.cancel()
+
+
+def multi_gpu_sections(args, torch, dist, fab, rank, world, device, flush):
+    """The multi-GPU workloads BASELINE.json names, measured and parity-checked inside the driver's own `--gpus N` run:
+    configs 4 and 3 at global size, B*H sharded (strong scaling, no collective), and config 5 as a ring."""
+    res = {}
+    peaks = load_peaks()
+    for key, fn in (("c4_sharded", lambda: sharded_strong(torch, dist, fab, "C4", rank, world, device, flush, peaks)),
+                    ("c3_sharded", lambda: sharded_strong(torch, dist, fab, "C3", rank, world, device, flush, peaks)),
+                    ("c5_ring", lambda: ring_c5(torch, dist, fab, rank, world, device, peaks))):
+        try:
+            res[key] = fn()
+        except Exception as e:  # a failure here must not take the headline line with it
+            res[key] = {"error": repr(e)[:300]}
+        torch.cuda.synchronize()
+    return res
+
+
+def sharded_strong(torch, dist, fab, name, rank, world, device, flush, peaks, steps=10):
+    """Config `name` at its GLOBAL size, the flattened B*H axis cut into `world` contiguous slices (no data-path collective)."""
+    B, H, N, d, dtype = WORKLOADS[name]
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    es = 2 if dtype == "bf16" else 4
+    g = torch.Generator(device=device).manual_seed(4242)          # the same global tensors on every rank
+    q, k, v = (torch.randn(B * H, N, d, device=device, generator=g).to(tdt) for _ in range(3))
+    s0, s1 = fab.bh_shard_range(B * H, rank, world)
+    qs, ks, vs = q[s0:s1], k[s0:s1], v[s0:s1]
+    scale = 1.0 / math.sqrt(d)
+    # parity (1): this rank's shard == the same rows of the unsharded forward, bit for bit (batch-invariant scheduling)
+    o_full = fab.attention(q, k, v, scale=scale, batch_invariant=True)
+    bit_equal = bool(torch.equal(fab.attention(qs, ks, vs, scale=scale, batch_invariant=True), o_full[s0:s1]))
+    # parity (2): default scheduling, 64 sampled rows per head against fp64 over all keys
+    o_sh, lse_sh = fab.attention(qs, ks, vs, scale=scale, return_lse=True)
+    err_o, err_l = fp64_rows_check(torch, qs[None], ks[None], vs[None], o_sh[None], lse_sh[None], scale, 64, 7 + rank)
+    out_n, out_1 = torch.empty_like(qs), torch.empty_like(q)
+    ms_n = time_kernel(torch, lambda: fab.attention(qs, ks, vs, scale=scale, out=out_n), steps, 3, flush)
+    ms_1 = time_kernel(torch, lambda: fab.attention(q, k, v, scale=scale, out=out_1), steps, 3, flush)
+    t_max = torch.tensor([sum(ms_n) / steps, err_o, err_l, 0.0 if bit_equal else 1.0], dtype=torch.float64, device=device)
+    dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    t_sum = torch.tensor([sum(ms_1) / steps], dtype=torch.float64, device=device)
+    dist.all_reduce(t_sum)
+    t_n, err_o, err_l, not_equal = t_max.tolist()
+    t_1 = float(t_sum[0]) / world
+    fl = flops_of(B, H, N, d)
+    peak = peaks["bf16"] if dtype == "bf16" else peaks["bf16"] / 2
+    tol = 2e-2 if dtype == "bf16" else 1e-3
+    return {"workload": f"{name}: B={B} H={H} d={d} N={N} {dtype}, global B*H={B * H} cut into {world} slices of {s1 - s0}, no collective",
+            "scaling": "strong", "ms": round(t_n, 5), "tflops_total": round(fl / t_n * 1e-9, 1),
+            "frac_tensor_peak_per_gpu": round(fl / world / t_n * 1e-9 / peak, 4),
+            "hbm_gbs_per_gpu": round(bytes_of(B, H, N, d, es) / world / t_n * 1e-6, 1),
+            "ms_one_gpu_same_run": round(t_1, 5), "speedup_vs_one_gpu": round(t_1 / t_n, 3), "efficiency": round(t_1 / (world * t_n), 4),
+            "timing": "CUDA events, L2 flushed before every step, 10 steps, max over ranks",
+            "parity": {"shard_bit_equal_to_unsharded_forward": not_equal == 0.0, "max_abs_err_o_vs_fp64_sampled_rows": err_o,
+                       "max_abs_err_lse_vs_fp64_sampled_rows": err_l, "rows_per_head": 64, "tolerance_o": tol,
+                       "ok": bool(not_equal == 0.0 and err_o < tol)}}
+
+
+def ring_c5(torch, dist, fab, rank, world, device, peaks, steps=3):
+    """Config 5: B=1 H=32 d=128 N=131072 bf16, the sequence cut into `world` shards; K/V shards pulled from their owners over
+    NVLink by the copy engines while the kernel of the current step runs; every step's kernel merges into the running
+    (O, LSE) in its epilogue."""
+    H, N, d = 32, 131072, 128
+    n_loc = N // world
+    scale = 1.0 / math.sqrt(d)
+    g = torch.Generator(device=device).manual_seed(5151)          # the same full tensors on every rank (1.07 GB each)
+    qf, kf, vf = (torch.randn(1, H, N, d, device=device, generator=g).to(torch.bfloat16) for _ in range(3))
+    sl = slice(rank * n_loc, (rank + 1) * n_loc)
+    q, k, v = (t[:, :, sl].contiguous() for t in (qf, kf, vf))
+    del qf
+
+    def timed(f, reps, warm):
+        for _ in range(warm):
+            f()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(reps):
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            f()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / reps
+
+    launches0 = fab.launch_count()
+    o, lse = fab.ring_attention(q, k, v, transport="p2p")
+    launches = fab.launch_count() - launches0
+    # parity (1): this rank's ring result vs ONE kernel launch of its queries over the full key sequence
+    o_one, lse_one = fab.attention(q, kf, vf, scale=scale, return_lse=True)
+    d_o = float((o.float() - o_one.float()).abs().max())
+    d_l = float((lse - lse_one).abs().max())
+    # parity (2): 16 sampled rows per head against fp64 over all 131072 keys
+    err_o, err_l = fp64_rows_check(torch, q, kf, vf, o, lse, scale, 16, 100 + rank)
+    del o_one, lse_one, kf, vf
+    ms_ring = timed(lambda: fab.ring_attention(q, k, v, transport="p2p"), steps, 1)
+    ms_nccl = timed(lambda: fab.ring_attention(q, k, v, transport="nccl"), max(1, steps - 1), 1)
+
+    def local_only():   # the same kernels (merge fused in the epilogue) on the resident shard, no transfers
+        acc = list(fab.attention(q, k, v, scale=scale, return_lse=True, out_f32=True))
+        for s_ in range(1, world):
+            acc[0] = fab.attention(q, k, v, scale=scale, out_f32=s_ < world - 1, acc=(acc[0], acc[1]))
+
+    ms_local = timed(local_only, steps, 1)
+    t = torch.tensor([ms_ring, ms_nccl, ms_local, d_o, d_l, err_o, err_l], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_ring, ms_nccl, ms_local, d_o, d_l, err_o, err_l = t.tolist()
+    fl = 4.0 * H * float(N) * N * d
+    per_gpu = fl / world / ms_ring * 1e-9
+    return {"workload": f"C5: B=1 H={H} d={d} N={N} bf16 non-causal, sequence cut into {world} shards of {n_loc}",
+            "scaling": "strong", "transport": "p2p (copy-engine pulls from CUDA-IPC-mapped peer buffers over NVLink)",
+            "ms": round(ms_ring, 3), "tflops_total": round(fl / ms_ring * 1e-9, 1), "tflops_per_gpu": round(per_gpu, 1),
+            "frac_sustained_peak": round(per_gpu / peaks["bf16_sustained"], 4), "frac_burst_peak": round(per_gpu / peaks["bf16"], 4),
+            "ms_same_kernels_no_transfers": round(ms_local, 3), "overlap": round(ms_local / ms_ring, 4),
+            "ms_nccl_transport": round(ms_nccl, 3), "kernel_launches_per_forward": launches,
+            "kv_bytes_pulled_per_gpu": 2 * k.numel() * 2 * (world - 1),
+            "timing": f"CUDA events around one ring forward, barrier before each, mean of {steps}, max over ranks",
+            "parity": {"max_abs_diff_o_vs_one_kernel_over_full_sequence": d_o, "max_abs_diff_lse_vs_one_kernel": d_l,
+                       "max_abs_err_o_vs_fp64_sampled_rows": err_o, "max_abs_err_lse_vs_fp64_sampled_rows": err_l, "rows_per_head": 16,
+                       "tolerance_o": 2e-2, "ok": bool(d_o < 2e-2 and err_o < 2e-2 and err_l < 2e-3)}}
 
 
 def run_ring(args, torch, dist, rank, world, device):
@@ -368,14 +646,14 @@ def run_ring(args, torch, dist, rank, world, device):
                      "frac": round(achieved / peaks["bf16_sustained"], 4), "traffic": None,
                      "peak_source": peaks["src"] + " bf16_tflops_sustained (per GPU; long step under the power cap)",
                      "frac_of_burst_peak": round(achieved / peaks["bf16"], 4),
-                     "kernel": "fa_fwd_sm100_kernel (bf16 d=128, fp32 partial output) x ring steps + fa_merge_kernel"},
+                     "kernel": "fa_fwd_sm100_kernel (bf16 d=128) x ring steps, each merging into the running (O, LSE) in its epilogue"},
     }
 
 
-def run_reference(args, torch, rank, world, device):
-    """The reference arm: its own forward(Q,K,V,causal) (scale fixed at 1.0 inside, src/flashattention.cu:593)."""
-    if rank != 0:
-        return None
+def run_reference(args, torch, dist, rank, world, device):
+    """The reference arm: its own forward(Q,K,V,causal) (scale fixed at 1.0 inside, src/flashattention.cu:593).  Its
+    implementation of this path is a CUDA kernel, so at N > 1 EVERY rank runs it on its own GPU on the same per-GPU workload as
+    our arm (weak scaling, max over ranks): the driver's same-N ratio then compares N GPUs with N GPUs."""
     from oracle import fa_oracle
 
     long_seq = args.workload == "C5"     # one forward of the reference kernel takes ~15 s at N = 131072: one warm-up, one step
@@ -386,34 +664,48 @@ def run_reference(args, torch, rank, world, device):
             "scaling": "weak", "vs_baseline": None, "data": "synthetic", "impl": "reference"}
     ext = fa_oracle.load_ref_torch_ext(d)  # bf16 workloads: the reference runs fp32 copies, it has no bf16 path
     if ext is not None and torch.cuda.is_available():
-        g = torch.Generator().manual_seed(1234)
+        g = torch.Generator().manual_seed(1234 + rank)
         hosts = [torch.randn(B * H, N, d, generator=g).pin_memory() for _ in range(3)]
         q, k, v = (h.to(device) for h in hosts)
         flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
-        steps = 1 if long_seq else max(1, min(args.steps, 10))
-        warm = 1 if long_seq else max(1, min(args.warmup, 3))
+        steps = 1 if long_seq else max(1, args.steps)          # one forward takes ~15 s at N = 131072
+        warm = 1 if long_seq else max(1, args.warmup)
+        if world > 1:
+            dist.barrier()
         ms = time_kernel(torch, lambda: ext.forward(q, k, v, False), steps, warm, flush)
         ms_per_step = sum(ms) / len(ms)
         o_host = torch.empty(B * H, N, d).pin_memory()
+        e2e_steps = 1 if long_seq else max(1, min(steps, 10))
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
-        e2e_steps = max(1, min(steps, 3))
         for _ in range(e2e_steps):
             dq, dk, dv = (h.to(device, non_blocking=True) for h in hosts)
             o_host.copy_(ext.forward(dq, dk, dv, False))
             torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([ms_per_step, e2e_s], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_per_step, e2e_s = t.tolist()
+        if rank != 0:
+            return None
+        fl = fl * world
         base.update({"value": round(fl / (ms_per_step * 1e-3) * 1e-12, 3), "ms_per_step": round(ms_per_step, 4), "steps": steps, "warmup": warm,
                      "dtype": "f32", "config": {"workload": f"{args.workload}: B={B} H={H} d={d} N={N} fp32 non-causal; reference CUDA kernel "
                                                             "flash_tiled_coarse rebuilt for sm_100a (oracle/_ref), its forward() incl. torch::zeros + cudaDeviceSynchronize, scale fixed at 1.0"},
                      "e2e": {"value": round(fl / e2e_s * 1e-12, 3), "unit": "TFLOP/s", "ms_per_step": round(e2e_s * 1e3, 3),
-                             "h2d_bytes_per_step": 3 * q.numel() * 4, "d2h_bytes_per_step": q.numel() * 4},
+                             "h2d_bytes_per_step": 3 * q.numel() * 4, "d2h_bytes_per_step": q.numel() * 4, "steps": e2e_steps,
+                             "host_binding": HOST_BINDING},
                      "cpu_baseline": reference_cpu_loop() or {
                          "value": None, "unit": "TFLOP/s", "cores": 0, "kind": "reference",
                          "sample": "the reference for this path is a CUDA kernel; it ran on the GPU, not on host cores"}})
         base["cpu_baseline"]["note"] = ("the reference's implementation of this path is a CUDA kernel: `value` and `e2e` of this line are "
                                         "that kernel on the same GPU; cpu_baseline is the only CPU code the reference has for it")
         return base
-    # no reference build on this box: time the oracle's CPU port of the same algorithm on a bounded sample
+    # no reference build on this box: time the oracle's CPU port of the same algorithm on a bounded sample (rank 0 only)
+    if rank != 0:
+        return None
     import numpy as np
 
     n_s = min(N, 2048)
@@ -453,29 +745,40 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference" and rank != 0:
-        return 0
     if not torch.cuda.is_available():
         if args.impl == "reference":
-            print(json.dumps(run_reference(args, torch, 0, world, None)))
+            if rank == 0:
+                print(json.dumps(run_reference(args, torch, dist, 0, world, None)))
             return 0
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    # cores / NUMA node first: the pinned host buffers allocated below land where this process runs
+    HOST_BINDING.clear()
+    HOST_BINDING.update(pin_to_gpu_numa(local, world))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    if world > 1 and args.impl == "ours":
+    if world > 1:
+        import datetime
+
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=300))
     try:
         if args.impl == "ours" and args.workload == "C5":
             line = run_ring(args, torch, dist, rank, world, device)
         elif args.impl == "ours":
             line = run_ours(args, torch, dist, rank, world, device)
         else:
-            line = run_reference(args, torch, rank, world, device)
+            line = run_reference(args, torch, dist, rank, world, device)
         if line is not None:
             print(json.dumps(line), flush=True)
     finally:
-        if world > 1 and args.impl == "ours" and dist.is_initialized():
+        if world > 1 and dist.is_initialized():
+            if args.impl == "ours":
+                try:
+                    import flashattention_c_b200 as fab
+
+                    fab.ring_p2p_release()      # collective: unmap peers' K/V buffers before anyone frees its own
+                except Exception:
+                    pass
             dist.destroy_process_group()
     return 0
 

@@ -67,7 +67,7 @@ def _strides_bhn(t: torch.Tensor):
 
 
 def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False, impl=_lib.FA_IMPL_AUTO, out=None,
-              batch_invariant=False, precise=False):
+              batch_invariant=False, precise=False, acc=None):
     """O = softmax(scale * Q K^T [+ causal mask]) V.   scale defaults to 1/sqrt(d).
 
     Q, K, V: CUDA tensors [B*H, N, d] or [B, H, N, d], float32, bfloat16 or float16; strided views with a contiguous last axis
@@ -77,6 +77,10 @@ def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False
     launch (alone, in a larger batch, on another rank of a B x H sharded job); costs the split-KV tail optimisation.
     precise: FA_FLAG_PRECISE — float32 inputs only: fp32-grade contractions ("3xTF32": hi/lo operand split, three tcgen05 MMAs
     per contraction) instead of plain tf32; head dims <= 64 on the tensor cores, larger ones on the CUDA-core kernel.
+    acc: (O_acc, LSE_acc) — accumulate mode: an earlier normalised partial of the same queries over other keys (float32,
+    contiguous, shapes of O and LSE) is merged into this call's result by the log-sum-exp rule inside the kernel's epilogue.
+    With a float32 result (float32 inputs, or out_f32) and no `out`, O_acc is updated in place and returned; LSE_acc is always
+    updated in place (and returned if return_lse).  This is one step of the ring forward (ring.py).
     """
     b, h, nq, nk, d = _shape4(Q, K, V)
     Q, K, V = _tma_view(Q), _tma_view(K), _tma_view(V)
@@ -84,10 +88,20 @@ def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False
         scale = 1.0 / math.sqrt(d)
     with torch.cuda.device(Q.device):
         o_dtype = torch.float32 if out_f32 else Q.dtype
+        if acc is not None:
+            o_acc, lse_acc = acc
+            if (o_acc.dtype != torch.float32 or lse_acc.dtype != torch.float32 or o_acc.shape != Q.shape or lse_acc.shape != Q.shape[:-1]
+                    or not o_acc.is_contiguous() or not lse_acc.is_contiguous() or o_acc.device != Q.device or lse_acc.device != Q.device):
+                raise FaError("acc = (O_acc, LSE_acc) must be contiguous float32 CUDA tensors shaped like O and LSE")
+            if out is None and o_dtype == torch.float32:
+                out = o_acc
         O = out if out is not None else torch.empty(Q.shape, dtype=o_dtype, device=Q.device)
         if out is not None and (O.shape != Q.shape or O.dtype != o_dtype or not O.is_contiguous()):
             raise FaError("out tensor has the wrong shape/dtype or is not contiguous")
-        lse = torch.empty(Q.shape[:-1], dtype=torch.float32, device=Q.device) if return_lse else None
+        if acc is not None:
+            lse = acc[1]
+        else:
+            lse = torch.empty(Q.shape[:-1], dtype=torch.float32, device=Q.device) if return_lse else None
         p = FaParams()
         p.q, p.k, p.v, p.o = Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr()
         p.lse = lse.data_ptr() if lse is not None else None
@@ -102,6 +116,8 @@ def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False
         p.o_stride_n, p.o_stride_h, p.o_stride_b = d, nq * d, h * nq * d
         p.impl = int(impl)
         p.flags = (_lib.FA_FLAG_BATCH_INVARIANT if batch_invariant else 0) | (_lib.FA_FLAG_PRECISE if precise else 0)
+        if acc is not None:
+            p.o_acc, p.lse_acc = acc[0].data_ptr(), acc[1].data_ptr()
         check(lib().fa_forward_ex(ctypes.byref(p), ctypes.c_void_p(_stream_ptr(Q.device))), "fa_forward_ex")
     return (O, lse) if return_lse else O
 

@@ -299,6 +299,7 @@ int run_tc(const fa_params* p, cudaStream_t st) {
   fp.o_ptr = p->o;
   fp.o_sb = p->o_stride_b; fp.o_sh = p->o_stride_h; fp.o_sn = p->o_stride_n;
   fp.o_row_bytes = p->head_dim * out_sz;
+  fp.acc_o = p->o_acc; fp.acc_lse = p->lse_acc; fp.head_dim = p->head_dim;
   {
     // whole waves of 256-row CTAs; a remainder of at most SMs/2 blocks runs as twice as many 128-row CTAs (one wave)
     const int64_t nb = (int64_t)fp.num_m_blocks * fp.heads * fp.batch;
@@ -470,6 +471,8 @@ int fa_forward_ex(const fa_params* p, void* stream) {
   if (!(p->scale > 0.f) || !std::isfinite(p->scale)) return FA_ERR_INVALID_ARG;
   if (p->n_q > 0x7fffffff || p->n_k > 0x7fffffff || p->batch > 0x7fffffff || p->heads > 0x7fffffff) return FA_ERR_INVALID_ARG;
   if (p->o_f32 && p->dtype == FA_F32) return FA_ERR_INVALID_ARG;   // fp32 inputs already give fp32 O
+  if ((p->o_acc == nullptr) != (p->lse_acc == nullptr)) return FA_ERR_INVALID_ARG;
+  if (p->o_acc && ((reinterpret_cast<uintptr_t>(p->o_acc) & 15) || p->head_dim % 4)) return FA_ERR_ALIGNMENT;
   int major = 0;
   int rc = probe_device(&major);
   if (rc) return rc;
@@ -481,6 +484,7 @@ int fa_forward_ex(const fa_params* p, void* stream) {
     if (!tc_supported(p)) return FA_ERR_UNSUPPORTED;
     rc = run_tc(p, st);
   } else if (impl == FA_IMPL_SIMT) {
+    if (p->o_acc) return FA_ERR_UNSUPPORTED;   // accumulate mode lives in the tcgen05 kernel's epilogue
     rc = run_simt(p, st);
   } else {
     return FA_ERR_INVALID_ARG;

@@ -170,6 +170,14 @@ struct FwdParams {
   void* o_ptr;        // O in global memory with its element strides: only for rows that see no key (zeros, no staging buffer)
   int64_t o_sb, o_sh, o_sn;
   int o_row_bytes;    // head_dim * sizeof(output element), a multiple of 16
+  // Accumulate mode (the steps of a ring forward after the first): an earlier partial result over other keys — O_acc fp32
+  // [batch, heads, n_q, head_dim] contiguous, already normalised, and its LSE_acc [batch, heads, n_q] — is folded into this
+  // launch's result by the log-sum-exp rule in the epilogue, before the O tile is staged:  lse = log(e^lse_acc + e^lse_new),
+  // O = O_acc e^(lse_acc - lse) + O_new e^(lse_new - lse).  O may be O_acc itself (each tile is read by the CTA that
+  // overwrites it, before it does) and `lse` may be LSE_acc.  nullptr: plain forward.
+  const float* acc_o;
+  const float* acc_lse;
+  int head_dim;       // true head dim (<= the instance's): row pitch of O_acc
 };
 constexpr int kTraceSteps = 48;
 
@@ -1090,6 +1098,29 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           lse_val = l_all > 0.f ? m_all * p.scale + logf(l_all) : -INFINITY;
         }
       }
+      // accumulate mode: weights of the earlier partial and of this launch's result in the merged row
+      float w_acc = 0.f;
+      const float* acc_row = nullptr;
+      if (p.acc_o != nullptr && stores) {
+        float w_new = 1.f;
+        if (q_row < p.n_q) {
+          const int64_t row_idx = (static_cast<int64_t>(w.batch) * p.heads + w.head) * p.n_q + q_row;
+          acc_row = p.acc_o + row_idx * p.head_dim;
+          const float la = p.acc_lse[row_idx], lb = lse_val;
+          const float mx = fmaxf(la, lb);
+          if (mx == -INFINITY) {
+            w_new = 0.f;
+          } else {
+            const float ea = expf(la - mx), eb = expf(lb - mx);
+            const float inv = 1.0f / (ea + eb);
+            w_acc = ea * inv;
+            w_new = eb * inv;
+            lse_val = mx + logf(ea + eb);
+          }
+        }
+        f_self *= w_new;
+        f_other *= w_new;
+      }
       const uint32_t stage = sQ + T::q_tile(set * 2 + t) * T::kTileBytes;   // kDChunks boxes of 16 KB (slot B of a one-slot
                                                                             // instance never stores: `stores` below)
       const uint32_t row_off = r * 128;
@@ -1129,6 +1160,20 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 tc_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(fmaf(__uint_as_float(ob[i]), f_other, __uint_as_float(o[i])));
+              }
+              if (acc_row != nullptr) {
+                // this row's 32 columns of the earlier partial, straight from global memory (L2): 512 B of one row per
+                // thread, once per item — noise next to the K/V stream of the item's main loop
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  if (cbase + 4 * g < p.head_dim) {
+                    const float4 a = *reinterpret_cast<const float4*>(acc_row + cbase + 4 * g);
+                    o[4 * g] = __float_as_uint(fmaf(a.x, w_acc, __uint_as_float(o[4 * g])));
+                    o[4 * g + 1] = __float_as_uint(fmaf(a.y, w_acc, __uint_as_float(o[4 * g + 1])));
+                    o[4 * g + 2] = __float_as_uint(fmaf(a.z, w_acc, __uint_as_float(o[4 * g + 2])));
+                    o[4 * g + 3] = __float_as_uint(fmaf(a.w, w_acc, __uint_as_float(o[4 * g + 3])));
+                  }
+                }
               }
               if (cbase == kLastCol0 && n_mine > 0) {
                 // last TMEM read of this item: the MMA warp may overwrite O_t (and O_B after a merge) with the next item's

@@ -230,24 +230,71 @@ def _p2p_state(k, group):
     return st
 
 
-def _ring_pull(st, q, k, v, causal, zz, c, attn, merge, rank, world):
-    """The ring forward over a pull transport `st` (see _P2PState).  Returns the fp32 accumulator and the LSE."""
+def ring_calls(rank, world, causal, zz):
+    """Every attention call of rank `rank`'s ring forward, in order: (source rank of the K/V shard, accumulator 0/1, query half
+    or None for the whole shard, key range 'lo'/'all', causal flag, last call into that accumulator).  A causal ring with
+    contiguous shards never looks at later ranks' shards; the zig-zag ring keeps one accumulator per query chunk."""
+    calls = []
+    for _, src in ring_schedule(rank, world):
+        if zz:
+            calls += [(src, hq, hq, keys, cz) for hq, keys, cz in zigzag_step_plan(rank, src)]
+        elif not causal or src <= rank:
+            calls.append((src, 0, None, "all", bool(causal and src == rank)))
+    last = {}
+    for i, cl in enumerate(calls):
+        last[cl[1]] = i
+    return [cl + (last[cl[1]] == i,) for i, cl in enumerate(calls)]
+
+
+class _Partials:
+    """The running (O, LSE) of a ring forward, one per accumulator.  Two ways to fold a step in:
+    fused (the product path on GPUs) — the step's kernel takes the running partial as its accumulate input and merges in
+        its epilogue; steps before the last keep O in fp32 in place, the last one writes O in the caller's dtype: no merge
+        launches, no extra pass over O, no final cast;
+    unfused — `attn` produces an fp32 partial and `merge` folds it in (the CPU test seams; fa_merge_partials on a GPU)."""
+
+    def __init__(self, attn, merge, fused_scale=None):
+        self.attn, self.merge, self.fused_scale = attn, merge, fused_scale
+        self.acc = [None, None]
+
+    def step(self, slot, q_, k_, v_, causal, is_last):
+        from . import api
+
+        if self.fused_scale is None:
+            o_s, lse_s = self.attn(q_, k_, v_, causal)
+            self.acc[slot] = [o_s, lse_s] if self.acc[slot] is None else list(self.merge(self.acc[slot][0], self.acc[slot][1], o_s, lse_s))
+            return
+        f32_out = not is_last and q_.dtype != torch.float32
+        if self.acc[slot] is None:
+            self.acc[slot] = list(api.attention(q_, k_, v_, causal=causal, scale=self.fused_scale, return_lse=True, out_f32=f32_out))
+        else:
+            self.acc[slot][0] = api.attention(q_, k_, v_, causal=causal, scale=self.fused_scale, out_f32=f32_out, acc=tuple(self.acc[slot]))
+
+    def result(self, zz):
+        if zz:
+            return torch.cat([self.acc[0][0], self.acc[1][0]], dim=-2), torch.cat([self.acc[0][1], self.acc[1][1]], dim=-1)
+        return self.acc[0][0], self.acc[0][1]
+
+
+def _ring_pull(st, q, k, v, causal, zz, c, parts, rank, world):
+    """The ring forward over a pull transport `st` (see _P2PState).  Returns O (fp32 accumulator, or the final dtype when the
+    merges are fused into the kernels) and the LSE."""
     kc, vc = k.contiguous(), v.contiguous()
     st.publish(kc, vc)
-    # the remote shards this rank needs, in ring order (a causal ring with contiguous shards never looks at later ranks)
-    remote = [src for _, src in ring_schedule(rank, world)[1:] if zz or not causal or src < rank]
-    acc = [[None, None], [None, None]]   # zig-zag: one accumulator per query chunk; otherwise acc[0]
-
-    def accumulate(slot, o_s, lse_s):
-        acc[slot] = [o_s, lse_s] if acc[slot][0] is None else list(merge(acc[slot][0], acc[slot][1], o_s, lse_s))
+    calls = ring_calls(rank, world, causal, zz)
+    # the remote shards this rank needs, in ring order
+    remote = []
+    for cl in calls:
+        if cl[0] != rank and cl[0] not in remote:
+            remote.append(cl[0])
 
     def compute(src, k_s, v_s):
-        if zz:
-            for hq, keys, cz in zigzag_step_plan(rank, src):
-                kk, vv = (k_s, v_s) if keys == "all" else (k_s[..., :c, :], v_s[..., :c, :])
-                accumulate(hq, *attn(q[..., hq * c:(hq + 1) * c, :], kk, vv, cz))
-        else:
-            accumulate(0, *attn(q, k_s, v_s, bool(causal and src == rank)))
+        for s_, slot, hq, keys, cz, is_last in calls:
+            if s_ != src:
+                continue
+            q_ = q if hq is None else q[..., hq * c:(hq + 1) * c, :]
+            kk, vv = (k_s, v_s) if keys == "all" else (k_s[..., :c, :], v_s[..., :c, :])
+            parts.step(slot, q_, kk, vv, cz, is_last)
 
     if remote:
         st.prefetch(0, remote[0])
@@ -258,13 +305,11 @@ def _ring_pull(st, q, k, v, causal, zz, c, attn, merge, rank, world):
         compute(src, *st.acquire(i, src))
         st.release(i)
     st.finish()
-    if zz:
-        return torch.cat([acc[0][0], acc[1][0]], dim=-2), torch.cat([acc[0][1], acc[1][1]], dim=-1)
-    return acc[0][0], acc[0][1]
+    return parts.result(zz)
 
 
-def ring_attention(q, k, v, causal=False, scale=None, group=None, zigzag=False, transport=None, _attn=None, _merge=None,
-                   _finalize=None):
+def ring_attention(q, k, v, causal=False, scale=None, group=None, zigzag=False, transport=None, fuse_merge=True, _attn=None,
+                   _merge=None, _finalize=None):
     """Sequence-partitioned forward.  q, k, v: this rank's shards [B, H, N/P, d] (or [B*H, N/P, d]), rank r holding
     sequence positions [r*N/P, (r+1)*N/P) — or, with zigzag=True (causal only), chunks r and 2P-1-r of 2P
     (zigzag_shard).  Returns this rank's shard of O in q's dtype and the fp32 LSE, in the same layout as q.
@@ -284,20 +329,23 @@ def ring_attention(q, k, v, causal=False, scale=None, group=None, zigzag=False, 
     attn = _attn or (lambda q_, k_, v_, c_: api.attention(q_, k_, v_, causal=c_, scale=scale, return_lse=True, out_f32=True))
     merge = _merge or api.merge_partials
     on_gpu = q.is_cuda
+    # the product path folds every step's partial into the running one inside the attention kernel's epilogue; with injected
+    # arithmetic (the CPU tests) or fuse_merge=False the partials are merged by `merge` and cast at the end
+    fused = on_gpu and _attn is None and _merge is None and _finalize is None and fuse_merge
+    parts = _Partials(attn, merge, scale if fused else None)
     if zigzag and not causal:
         raise ValueError("zigzag sharding only makes sense for the causal ring")
     if zigzag and q.shape[-2] % 2:
         raise ValueError("a zig-zag shard holds two chunks of equal length")
     zz = zigzag and world > 1
     c = q.shape[-2] // 2
-    # zig-zag: separate accumulators for the two query chunks (each step touches one or both)
-    acc = [[None, None], [None, None]]
 
-    def zz_accumulate(half, o_s, lse_s):
-        if acc[half][0] is None:
-            acc[half] = [o_s, lse_s]
-        else:
-            acc[half] = list(merge(acc[half][0], acc[half][1], o_s, lse_s))
+    def finish(o_acc, lse_acc):
+        if _finalize is not None:
+            return _finalize(o_acc), lse_acc
+        if on_gpu and o_acc.dtype != q.dtype:
+            return api.cast_to_16(o_acc, q.dtype), lse_acc
+        return o_acc, lse_acc
 
     if world == 1:
         o, lse = attn(q, k, v, causal)
@@ -311,10 +359,7 @@ def ring_attention(q, k, v, causal=False, scale=None, group=None, zigzag=False, 
             raise ValueError("the p2p transport needs CUDA tensors")
         # a transport object (publish / prefetch / acquire / release / finish) is the CPU tests' stand-in for _P2PState
         st = _p2p_state(k, group) if transport == "p2p" else transport
-        o_acc, lse_acc = _ring_pull(st, q, k, v, causal, zz, c, attn, merge, rank, world)
-        if _finalize is not None:
-            return _finalize(o_acc), lse_acc
-        return (api.cast_to_16(o_acc, q.dtype) if (on_gpu and q.dtype != torch.float32) else o_acc), lse_acc
+        return finish(*_ring_pull(st, q, k, v, causal, zz, c, parts, rank, world))
 
     nxt = dist.get_global_rank(group, (rank + 1) % world) if group is not None else (rank + 1) % world
     prv = dist.get_global_rank(group, (rank - 1) % world) if group is not None else (rank - 1) % world
@@ -322,7 +367,7 @@ def ring_attention(q, k, v, causal=False, scale=None, group=None, zigzag=False, 
     spare = [(torch.empty_like(k_cur), torch.empty_like(v_cur)) for _ in range(2)]  # receive buffers, ping-pong
     main = torch.cuda.current_stream(q.device) if on_gpu else None
     comm = torch.cuda.Stream(device=q.device) if on_gpu else None
-    o_acc = lse_acc = None
+    calls = ring_calls(rank, world, causal, zz)
 
     for step, src in ring_schedule(rank, world):
         reqs = []
@@ -336,31 +381,18 @@ def ring_attention(q, k, v, causal=False, scale=None, group=None, zigzag=False, 
                     reqs = dist.batch_isend_irecv(ops)
             else:
                 reqs = dist.batch_isend_irecv(ops)
-        # local tile loop on the shard that is resident now (overlaps the transfer above)
-        if zz:
-            for half, keys, cz in zigzag_step_plan(rank, src):
-                q_h = q[..., half * c:(half + 1) * c, :]
-                k_s, v_s = (k_cur, v_cur) if keys == "all" else (k_cur[..., :c, :], v_cur[..., :c, :])
-                zz_accumulate(half, *attn(q_h, k_s, v_s, cz))
-        elif causal and src > rank:
-            pass  # every key of this shard is in the future of every local query
-        else:
-            o_s, lse_s = attn(q, k_cur, v_cur, bool(causal and src == rank))
-            if o_acc is None:
-                o_acc, lse_acc = o_s, lse_s
-            else:
-                o_acc, lse_acc = merge(o_acc, lse_acc, o_s, lse_s)
+        # local tile loop on the shard that is resident now (overlaps the transfer above); a causal ring with contiguous
+        # shards has no call for a later rank's shard: every key of it is in the future of every local query
+        for s_, slot, hq, keys, cz, is_last in calls:
+            if s_ != src:
+                continue
+            q_ = q if hq is None else q[..., hq * c:(hq + 1) * c, :]
+            k_s, v_s = (k_cur, v_cur) if keys == "all" else (k_cur[..., :c, :], v_cur[..., :c, :])
+            parts.step(slot, q_, k_s, v_s, cz, is_last)
         if step < world - 1:
             for r in reqs:
                 r.wait()
             if on_gpu:
                 main.wait_stream(comm)
             k_cur, v_cur = k_nxt, v_nxt
-    if zz:
-        o_acc = torch.cat([acc[0][0], acc[1][0]], dim=-2)
-        lse_acc = torch.cat([acc[0][1], acc[1][1]], dim=-1)
-    if _finalize is not None:
-        return _finalize(o_acc), lse_acc
-    if on_gpu and q.dtype != torch.float32:
-        return api.cast_to_16(o_acc, q.dtype), lse_acc
-    return o_acc, lse_acc
+    return finish(*parts.result(zz))

@@ -83,6 +83,13 @@ typedef struct fa_params {
   int64_t o_stride_b, o_stride_h, o_stride_n;
   int32_t impl;            /* 0 = automatic; FA_IMPL_TCGEN05 / FA_IMPL_SIMT force a kernel family (tests) */
   int32_t flags;           /* bit set of enum fa_flags (0 = defaults) */
+  /* Accumulate mode (tcgen05 kernel only; both NULL = plain forward).  o_acc: fp32 [batch, heads, n_q, head_dim]
+   * contiguous, lse_acc: fp32 [batch, heads, n_q] — an earlier, normalised partial result of the same queries over OTHER
+   * keys.  The kernel folds it into its own result by the log-sum-exp rule inside its epilogue (what fa_merge_partials
+   * does as a separate pass): O and LSE come out merged.  o may be o_acc and lse may be lse_acc (in place).  This is a
+   * ring-forward step: the merge costs no launch and no extra pass over O, and the last step can write 16-bit O directly. */
+  const float* o_acc;
+  const float* lse_acc;
 } fa_params;
 
 /*

@@ -205,3 +205,33 @@ def test_bench_reads_measured_peaks_or_states_the_fallback(tmp_path, monkeypatch
     (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps({"bf16_tflops": 1600.0, "hbm_gbs": 6500.0}))
     assert bench.load_peaks()["bf16_sustained"] == 1600.0        # older file without the sustained figure
     assert bench.flops_of(2, 8, 8192, 64) == 4.0 * 16 * 8192 * 8192 * 64 and bench.bytes_of(2, 8, 8192, 64, 4) == 4.0 * 16 * 8192 * 64 * 4
+
+
+def test_ring_calls_cover_every_visible_pair_once_and_flag_the_last_call():
+    """ring_calls: the attention calls of one rank's ring forward.  Every (query chunk, key chunk) pair that is visible is
+    covered exactly once, and exactly one call per accumulator — the last — is flagged (it writes the caller's dtype)."""
+    from flashattention_c_b200.ring import ring_calls
+
+    for world in (1, 2, 4, 8):
+        for rank in range(world):
+            calls = ring_calls(rank, world, False, False)
+            assert [c[0] for c in calls] == [(rank - s) % world for s in range(world)]
+            assert [c[5] for c in calls] == [False] * (world - 1) + [True] and all(c[1] == 0 and c[2] is None for c in calls)
+            calls = ring_calls(rank, world, True, False)
+            assert sorted(c[0] for c in calls) == list(range(rank + 1)) and calls[0][4] and not any(c[4] for c in calls[1:])
+            assert sum(c[5] for c in calls) == 1 and calls[-1][5]
+            if world == 1:
+                continue
+            calls = ring_calls(rank, world, True, True)
+            seen = set()
+            for src, slot, hq, keys, cz, is_last in calls:
+                assert slot == hq
+                qc = rank if hq == 0 else 2 * world - 1 - rank
+                for kc in ([src] if keys == "lo" else [src, 2 * world - 1 - src]):
+                    assert kc <= qc and (cz or kc < qc) and (qc, kc) not in seen
+                    seen.add((qc, kc))
+            want = {(qc, kc) for qc in (rank, 2 * world - 1 - rank) for kc in range(2 * world) if kc <= qc}
+            assert seen == want
+            for slot in (0, 1):
+                flags = [c[5] for c in calls if c[1] == slot]
+                assert flags[-1] and sum(flags) == 1

@@ -492,7 +492,7 @@ def test_multi_gpu_sharding_and_ring_over_nccl(cuda_device):
     assert lines[0]["bitwise_equal"]                           # FA_FLAG_BATCH_INVARIANT: sharded == unsharded, bit for bit
     assert lines[0]["default_mode_max_abs_diff"] < 2e-2        # default scheduling: within the bf16 tolerance
     ring = [l for l in lines if l["check"].startswith("ring_vs_single_gpu")]
-    assert len(ring) == 4 and all(l["ok"] for l in ring), ring
+    assert len(ring) == 8 and all(l["ok"] for l in ring), ring      # {p2p, nccl} x {bf16 d128, fp32 d64} x {full, causal}
     zz = [l for l in lines if l["check"].startswith("zigzag_causal_ring_vs_single_gpu")]
     assert len(zz) == 2 and all(l["ok"] for l in zz), zz
 
@@ -850,3 +850,70 @@ def test_reference_bench_script_runs_unmodified(cuda_device, extra):
     print(res.stdout[-2500:])
     assert res.returncode == 0, res.stderr[-3000:]
     assert "[Correctness] attn values sanity check: PASSED" in res.stdout
+
+
+# ------------------------------------------------------------------ round 2: merge fused into the kernel epilogue (ring steps)
+@pytest.mark.parametrize("dtype,d,n,P", [(torch.bfloat16, 128, 1024, 4), (torch.bfloat16, 96, 1000, 3), (torch.float32, 64, 1024, 4),
+                                          (torch.float32, 32, 600, 2), (torch.float16, 64, 640, 5), (torch.float32, 128, 515, 2),
+                                          (torch.bfloat16, 256, 512, 2)])
+def test_accumulate_mode_is_the_ring_merge(fab, oracle, cuda_device, dtype, d, n, P):
+    """Accumulate mode (fa_params.o_acc / lse_acc): the keys are cut into P shards on ONE GPU and every call after the first
+    takes the running (O, LSE) as its accumulate input — fp32 in place until the last call, which writes O in the inputs'
+    dtype.  Must equal the unpartitioned forward (oracle), and the unfused chain kernel -> fa_merge_partials -> cast."""
+    B, H = 2, 3
+    q, k, v = seeded((B, H, n, d), 601), seeded((B, H, n, d), 602), seeded((B, H, n, d), 603)
+    if dtype != torch.float32:
+        q, k, v = (torch.from_numpy(x).to(dtype).float().numpy() for x in (q, k, v))
+    tq, tk, tv = (torch.from_numpy(x).to(cuda_device).to(dtype) for x in (q, k, v))
+    scale = 1 / math.sqrt(d)
+    cuts = [round(i * n / P) for i in range(P + 1)]
+    acc = None
+    o_unf = lse_unf = None
+    launches0 = fab.launch_count()
+    for s in range(P):
+        ks, vs = tk[:, :, cuts[s]:cuts[s + 1]], tv[:, :, cuts[s]:cuts[s + 1]]
+        last = s == P - 1
+        f32_out = not last and dtype != torch.float32
+        if acc is None:
+            acc = list(fab.attention(tq, ks, vs, scale=scale, return_lse=True, out_f32=f32_out))
+        else:
+            acc[0] = fab.attention(tq, ks, vs, scale=scale, out_f32=f32_out, acc=(acc[0], acc[1]))
+        assert fab.last_impl() == fab.FA_IMPL_TCGEN05
+    assert fab.launch_count() - launches0 == P          # one kernel per shard: no merge, no cast
+    for s in range(P):
+        o_s, lse_s = fab.attention(tq, tk[:, :, cuts[s]:cuts[s + 1]], tv[:, :, cuts[s]:cuts[s + 1]], scale=scale, return_lse=True,
+                                   out_f32=dtype != torch.float32)
+        if o_unf is None:
+            o_unf, lse_unf = o_s, lse_s
+        else:
+            fab.merge_partials(o_unf, lse_unf, o_s, lse_s)
+    o_ref, lse_ref = oracle.f64(q, k, v, scale, False)
+    o = acc[0]
+    assert o.dtype == dtype
+    tol = TOL_BF16 if dtype != torch.float32 else TOL_TF32
+    assert np.abs(o.float().cpu().numpy() - o_ref).max() < tol
+    assert np.abs(acc[1].cpu().numpy() - lse_ref).max() < 2e-3
+    assert float((o.float() - o_unf.to(dtype).float()).abs().max()) < (1e-5 if dtype == torch.float32 else 2e-2)
+    assert float((acc[1] - lse_unf).abs().max()) < 1e-5
+
+
+def test_accumulate_mode_causal_cross_length_and_masked_rows(fab, oracle, cuda_device):
+    """Two causal key shards with a bottom-right aligned mask: the first shard leaves the early rows without any key
+    (LSE_acc = -inf, O_acc = 0), the second step must still produce the exact rows."""
+    n, d = 512, 64
+    q, k, v = seeded((4, n, d), 611), seeded((4, n, d), 612), seeded((4, n, d), 613)
+    tq, tk, tv = (torch.from_numpy(x).to(cuda_device) for x in (q, k, v))
+    # rows [256, 512) of the causal problem: keys [0, 256) all visible (non-causal call), keys [256, 512) causal
+    o, lse = fab.attention(tq[:, 256:], tk[:, :256], tv[:, :256], scale=0.125, return_lse=True)
+    o = fab.attention(tq[:, 256:], tk[:, 256:], tv[:, 256:], causal=True, scale=0.125, acc=(o, lse))
+    o_ref, lse_ref = oracle.f64(q, k, v, 0.125, True)
+    assert tf32_err(o.cpu().numpy(), o_ref[:, 256:]) < TOL_TF32_FEWKEYS and np.abs(lse.cpu().numpy() - lse_ref[:, 256:]).max() < 5e-3
+    # all rows, shard order reversed: the first call (keys [256, 512), n_q = 512 > n_k = 256) leaves rows [0, 256) empty
+    o, lse = fab.attention(tq, tk[:, 256:], tv[:, 256:], causal=True, scale=0.125, return_lse=True)
+    assert torch.isneginf(lse[:, :256]).all() and (o[:, :256] == 0).all()
+    o2 = fab.attention(tq, tk[:, :256], tv[:, :256], causal=False, scale=0.125, acc=(o, lse))
+    # second call: every row sees keys [0, 256) — but rows < 256 must only see keys <= row: emulate with a causal call on them
+    o_lo, lse_lo = fab.attention(tq[:, :256], tk[:, :256], tv[:, :256], causal=True, scale=0.125, return_lse=True)
+    assert o2.data_ptr() == o.data_ptr()
+    assert tf32_err(o2[:, 256:].cpu().numpy(), o_ref[:, 256:]) < TOL_TF32_FEWKEYS
+    assert tf32_err(o_lo.cpu().numpy(), o_ref[:, :256]) < TOL_TF32_FEWKEYS
