@@ -88,6 +88,12 @@
                              // of P has arrived every S column is in registers — so the upper half of the next Q*K^T (keys 64..127
                              // -> columns [64, 128)) is issued right behind the first piece's P*V instead of after the second's
 #endif
+#ifndef FA_OPT_ROT_S
+#define FA_OPT_ROT_S 1       // two-slot instances with head dim <= 64: the S tiles of both slots rotate through THREE TMEM buffers
+                             // (3 * 128 + 2 * d <= 512 columns), so Q K^T of a slot's next step is issued a whole step early — behind
+                             // the other slot's P V, into the buffer that P V has just freed — and drops out of the slot's serial
+                             // chain softmax(j) -> P V(j) -> Q K^T(j+1) -> softmax(j+1): softmax(j+1) starts when softmax(j) ends
+#endif
 #ifndef FA_OPT_ROLL_MMA
 #define FA_OPT_ROLL_MMA 0    // 1: the k-step loops of the MMA warp stay rolled (smaller code for a warp that shares its instruction
                              // cache with the unrolled exp loops of the softmax warps)
@@ -228,14 +234,18 @@ struct FwdTraits {
   // relative error is what that mode exists to avoid)
   static constexpr int kPolyNum = kPrecise ? 0 : (kDChunks == 1 ? FA_POLY_NUM_NARROW : (kTF32 ? FA_POLY_NUM_TF32 : FA_POLY_NUM_BF16));
   static constexpr int kPolyDen = kDChunks == 1 ? FA_POLY_DEN_NARROW : (kTF32 ? FA_POLY_DEN_TF32 : FA_POLY_DEN_BF16);
+  static constexpr bool kRotS = (FA_OPT_ROT_S != 0) && kSlots == 2 && (FA_OPT_EARLY_S == 0) && (FA_OPT_EARLY_HI == 0) &&
+                                (3 * kBlockN + 2 * kHeadDim <= 512);
+  static constexpr int kSBufs = kRotS ? 3 : 2;   // S tile n = 2 * step + slot of an item lives in buffer n % kSBufs
   static constexpr int kSmemData = (kSlots * kQSets + kNBuf) * kTileBytes;
   static constexpr int kNumBarriers = 4 * kQSets /*q full, q free*/ + 2 * kNBuf + 2 /*s_full*/ + 4 /*p_full halves*/ +
                                       2 /*o_final*/ + 2 /*o_free*/ + 2 * kWorkQueue + 2 /*pv1 done*/ +
-                                      (kPrecise ? kNBuf + 2 : 0) /*lo copy of a K/V tile / of the Q tile written*/;
+                                      (kPrecise ? kNBuf + 2 : 0) /*lo copy of a K/V tile / of the Q tile written*/ +
+                                      (kRotS ? 6 : 0) /*s_full and p_full of the odd steps*/;
   static constexpr int kSmemBytes = kSmemData + kNumBarriers * 8 + 16 /*tmem ptr*/ + kWorkQueue * 4 + 2 * kBlockM * 4 /*m, l*/ +
                                     1024 /*alignment slack*/;
-  static constexpr int kTmemS = 0;        // + 128*t
-  static constexpr int kTmemO = 256;      // + kHeadDim*t
+  static constexpr int kTmemS = 0;        // + 128*t (kRotS: + 128 * (tile number % 3))
+  static constexpr int kTmemO = kRotS ? 384 : 256;      // + kHeadDim*t
   static constexpr int kTmemPLo = kBlockN;   // kPrecise: lo part of P, in the S columns of the (unused) slot B
   static constexpr int kP1Cols = (kBlockN - kSplitKeys) * kInSize / 4;   // TMEM columns of the second piece of P
   static constexpr int kTmemP1 = 256 + 2 * kHeadDim;                      // + kP1Cols*t (kEarlyS only)
@@ -244,7 +254,7 @@ struct FwdTraits {
   static constexpr bool kEarlyS = (FA_OPT_EARLY_S != 0) && !kPrecise && kSplitP && (256 + 2 * kHeadDim + 2 * kP1Cols <= 512);
   static_assert(kDChunks == 1 || kDChunks == 2 || kDChunks == 4, "tile row must be 128, 256 or 512 bytes");
   static_assert(!kPrecise || (kTF32 && kSlots == 1 && !kOutF32), "precise instances: fp32 operands, one slot (slot B's warps write the lo copies)");
-  static_assert(256 + kSlots * kHeadDim <= 512, "TMEM budget");
+  static_assert(kTmemO + kSlots * kHeadDim <= 512, "TMEM budget");
   static_assert(kSmemBytes <= 227 * 1024, "SMEM budget");
   // SMEM tile index of Q buffer qb = set * 2 + slot (the barrier index): one-slot instances have no tile for slot B
   __host__ __device__ static constexpr int q_tile(int qb) { return kSlots == 2 ? qb : (qb >> 1); }
@@ -311,6 +321,32 @@ FA_DEVINL Item decode_item(const FwdParams& p, int bid) {
   return it;
 }
 
+// Every MMA group of an item in issue order, for instances whose S tiles rotate through kSBufs TMEM buffers (kRotS).
+// Tile n = 2 * step + slot.  f(true, t, j): P_t(j) V -> O_t;  f(false, t, j): S_t(j) = Q_t K^T into buffer n % kSBufs.
+// S of tile n + kSBufs goes into the buffer that P V of tile n has just finished reading (the tensor pipe runs in issue
+// order), so every slot's S is a full step ahead of its softmax.  The TMA producer walks the same sequence to load the
+// K/V tiles in the order of their first use.
+template <int kSBufs, typename F>
+FA_DEVINL void for_each_mma(const Item& w, F&& f) {
+  const int n_tiles = 2 * w.n_max;
+#pragma unroll 1
+  for (int n = -kSBufs; n < n_tiles; ++n) {
+    if (n >= 0) {
+      const int t = n & 1, j = n >> 1;
+      if (j < w.n(t)) f(true, t, j);
+    }
+    const int m = n + kSBufs;
+    if (m < n_tiles) {
+      const int t = m & 1, j = m >> 1;
+      if (j < w.n(t)) f(false, t, j);
+    }
+  }
+}
+// In a 256-row item both slots read the same K/V tiles: slot A's use of tile j is the first (slot B's when A has no step j),
+// slot B's the last (slot A's when B has none).  In a split-KV item every slot has tiles of its own.
+FA_DEVINL bool kv_first_use(const Item& w, int t, int j) { return w.split || t == 0 || j >= w.n0; }
+FA_DEVINL bool kv_last_use(const Item& w, int t, int j) { return w.split || t == 1 || j >= w.n1; }
+
 // kF16 (16-bit instances only): the operands are IEEE fp16 instead of bf16 — same kind::f16 instruction, operand format 0
 // instead of 1; P <= 2^kRescaleThreshold by construction (lazy rescale), far inside the fp16 range.
 template <bool kTF32, int kHeadDim, bool kCausal, bool kOutF32, bool kF16 = false, bool kPrecise = false>
@@ -338,7 +374,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const uint32_t bar_pv1 = bar_wempty + 8 * kWorkQueue;       // [2]  second-piece P*V of slot t's latest step has completed
   const uint32_t bar_conv = bar_pv1 + 16;                     // [kNBuf]  kPrecise: lo copy of the K/V tile in ring slot i written
   const uint32_t bar_qconv = bar_conv + 8 * T::kNBuf;         // [2]      kPrecise: lo copy of the Q tile written ([1] unused)
-  const uint32_t s_tmem_ptr = kPrecise ? bar_qconv + 16 : bar_pv1 + 16;   // 16 bytes
+  const uint32_t bar_s_odd = bar_pv1 + 16;                    // [2]      kRotS: S of the odd steps (a slot's S runs a step ahead of its
+  const uint32_t bar_p_odd = bar_s_odd + 16;                  // [slot][half]    softmax, so consecutive steps need barriers of their own)
+  const uint32_t s_tmem_ptr = kPrecise ? bar_qconv + 16 : (T::kRotS ? bar_p_odd + 32 : bar_pv1 + 16);   // 16 bytes
   const uint32_t s_work = s_tmem_ptr + 16;                    // [kWorkQueue] item indices (-1 = no more work)
   const uint32_t s_ml = s_work + 4 * kWorkQueue;              // m[128], l[128] of slot B (split-KV merge)
 
@@ -371,6 +409,13 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_init(bar_wfull + 8 * i, 1);
       mbar_init(bar_wempty + 8 * i, 9);   // MMA warp + 8 softmax warps
     }
+    if constexpr (T::kRotS) {
+      for (int t = 0; t < 2; ++t) {
+        mbar_init(bar_s_odd + 8 * t, 1);
+        mbar_init(bar_p_odd + 16 * t, 128);
+        mbar_init(bar_p_odd + 16 * t + 8, 128);
+      }
+    }
     if constexpr (kPrecise) {
       for (int i = 0; i < T::kNBuf; ++i) mbar_init(bar_conv + 8 * i, 4);   // one arrival per warp of slot B
       mbar_init(bar_qconv, 4);
@@ -396,6 +441,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (threadIdx.x == 0) FA_TRACE_MISC(0, 1);
   if (threadIdx.x == 128) FA_TRACE_MISC(1, 1);
 
+  // s_full / p_full of step g of a slot (g counts the slot's K/V steps over all items).  kRotS: even and odd steps have
+  // barriers of their own — S_t(g+1) may complete before the softmax has waited for S_t(g), and P_t(g+1) may be delivered
+  // before the MMA warp has waited for P_t(g); a single barrier would then be two phases ahead of its waiter.
+  auto bar_s_at = [&](int t, int g) { return ((T::kRotS && (g & 1)) ? bar_s_odd : bar_s) + 8 * t; };
+  auto bar_p_at = [&](int t, int h, int g) { return ((T::kRotS && (g & 1)) ? bar_p_odd : bar_p) + 16 * t + 8 * h; };
+  auto par_at = [&](int g) { return static_cast<uint32_t>(T::kRotS ? (g >> 1) & 1 : g & 1); };
   // consumer side of the item queue: every lane of the warp reads the item, one lane releases the queue slot
   auto next_item = [&](int seq) -> int {
     if (seq == 0) return static_cast<int>(blockIdx.x);
@@ -486,7 +537,12 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           load_q();
           q_done = true;
         }
-        if (!w.split) {
+        if constexpr (T::kRotS) {
+          // tiles in the order of their first use by the MMA warp: K_0, K_1, V_0, K_2, V_1, ... (K runs a step ahead)
+          for_each_mma<T::kSBufs>(w, [&](bool pv, int t, int j) {
+            if (kv_first_use(w, t, j)) kv(pv ? &tm_v : &tm_k, (t == 0 ? 0 : w.kv_first1) + j);
+          });
+        } else if (!w.split) {
           for (int j = 0; j < w.n_max; ++j) {   // K_0, V_0, K_1, V_1, ... shared by both Q tiles
             kv(&tm_k, j);
             kv(&tm_v, j);
@@ -585,6 +641,25 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           mma_ts<kTF32>(d, a + ks * 8, vd + lo16 + static_cast<uint32_t>(ks * (T::kUmmaK * 128 / 16)), idesc_pv, 1u);
       }
     };
+    // the same two with explicit TMEM addresses (kRotS: the S buffer changes from step to step)
+    auto issue_s_at = [&](uint32_t d, int qbuf, int buf) {
+      const uint64_t qd = sdesc_at(hi_kmajor, sQ + T::q_tile(qbuf) * T::kTileBytes);
+      const uint64_t kd = sdesc_at(hi_kmajor, sKV + buf * T::kTileBytes);
+      FA_MMA_UNROLL
+      for (int kk = 0; kk < kKStepsS; ++kk) {
+        const uint32_t off16 = ((kk >> 2) * kChunkBytes + (kk & 3) * 32) >> 4;
+        mma_ss<kTF32>(d, qd + off16, kd + off16, idesc_s, kk > 0 ? 1u : 0u);
+      }
+    };
+    auto issue_pv_at = [&](uint32_t d, uint32_t a, int buf, bool accumulate, int ks0, int ks1) {
+      const uint64_t vd = sdesc_at(hi_mnmajor, sKV + buf * T::kTileBytes);
+      FA_MMA_UNROLL
+      for (int ks = ks0; ks < ks1; ++ks) {
+        mma_ts<kTF32>(d, a + ks * 8, vd + static_cast<uint32_t>(ks * (T::kUmmaK * 128 / 16)), idesc_pv,
+                      (accumulate || ks > 0) ? 1u : 0u);
+      }
+    };
+    int gs_a = 0, gs_b = 0, gp_a = 0, gp_b = 0;   // kRotS: S tiles issued / P V groups issued per slot, over all items
     int ring = 0;                 // K/V ring index, same sequence as the producer's
     uint32_t p_par = 0;           // bit t: parity of the next bar_p[t] phase (one phase per K/V step of slot t, over all items)
     uint32_t q_par = 0;           // bit qb: parity of the next bar_q[qb] phase (one phase per Q tile loaded into buffer qb)
@@ -692,7 +767,55 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
       }
       if (seq == 0) FA_TRACE_MISC(2, 1);
-      if (!w.split) {
+      if constexpr (T::kRotS) {
+        // ---- S tiles rotate through three buffers: see for_each_mma ----
+        bool ofree_done = false;
+        int k_sh = 0, v_sh = 0;   // ring index of the K / V tile the two slots share (set by its first user)
+        for_each_mma<T::kSBufs>(w, [&](bool pv, int t, int j) {
+          const bool first_use = kv_first_use(w, t, j), last_use = kv_last_use(w, t, j);
+          if (first_use) {
+            if (pv) v_sh = ring++; else k_sh = ring++;
+          }
+          const int idx = pv ? v_sh : k_sh;
+          const int buf = idx % T::kNBuf;
+          if (first_use) {
+            wait_full(idx);
+            tc_fence_after();
+          }
+          const uint32_t s_tile = tmem_base + T::kTmemS + static_cast<uint32_t>(((2 * j + t) % T::kSBufs) * kBlockN);
+          if (!pv) {
+            const int g = t == 0 ? gs_a++ : gs_b++;
+            if (elect_one_sync()) {
+              issue_s_at(s_tile, set * 2 + (w.split ? 0 : t), buf);
+              tc_commit(bar_s_at(t, g));
+              if (last_use) tc_commit(bar_empty + 8 * buf);
+            }
+            __syncwarp();
+          } else {
+            if (!ofree_done) {   // the first P V of an item overwrites O_t: the previous item's epilogues must have read it
+              wait_ofree();
+              ofree_done = true;
+            }
+            const int g = t == 0 ? gp_a++ : gp_b++;
+            const uint32_t o_acc = tmem_base + T::kTmemO + static_cast<uint32_t>(t * kHeadDim);
+            if constexpr (T::kSplitP) {
+              mbar_wait(bar_p_at(t, 0, g), par_at(g), TAG_P_FULL);
+              tc_fence_after();
+              if (elect_one_sync()) issue_pv_at(o_acc, s_tile, buf, j > 0, 0, kKStepsSplit);
+              __syncwarp();
+            }
+            mbar_wait(bar_p_at(t, 1, g), par_at(g), TAG_P_FULL);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              issue_pv_at(o_acc, s_tile, buf, j > 0, T::kSplitP ? kKStepsSplit : 0, kKStepsPV);
+              tc_commit(bar_pv1 + 8 * t);     // O_t holds all of step j (the softmax rescales O_t only behind this)
+              if (last_use) tc_commit(bar_empty + 8 * buf);
+              if (j == w.n(t) - 1) tc_commit(bar_o + 8 * t);
+            }
+            __syncwarp();
+          }
+        });
+      } else if (!w.split) {
         // ---- two Q tiles share every K/V tile: K_j then V_j in ring order ----
         const int r0 = ring;
         ring += 2 * w.n_max;
@@ -837,7 +960,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int t = warp >> 2;                       // tile slot of this warpgroup
     const int r = (warp & 3) * 32 + lane;          // row within the tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem_base + lane_base + T::kTmemS + t * kBlockN;
+    const uint32_t tS_fixed = tmem_base + lane_base + T::kTmemS + t * kBlockN;
     const uint32_t tO = tmem_base + lane_base + T::kTmemO + t * kHeadDim;
     const uint32_t tO_other = tmem_base + lane_base + T::kTmemO + (t ^ 1) * kHeadDim;
     const uint32_t tP1 = tmem_base + lane_base + T::kTmemP1 + t * T::kP1Cols;   // second piece of P (kEarlyS)
@@ -941,8 +1064,10 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       for (int j = 0; j < n_mine; ++j) {
         const int g = steps++;
         if (tracer) FA_TRACE_AT(t, g, 0);
-        mbar_wait(bar_s + 8 * t, g & 1, TAG_S_FULL);
+        mbar_wait(bar_s_at(t, g), par_at(g), TAG_S_FULL);
         tc_fence_after();
+        // this step's S tile (P overwrites it in place): fixed per slot, or tile number % 3 of the rotating buffers
+        const uint32_t tS = T::kRotS ? tmem_base + lane_base + T::kTmemS + static_cast<uint32_t>(((2 * j + t) % T::kSBufs) * kBlockN) : tS_fixed;
         if (tracer) FA_TRACE_AT(t, g, 1);
         float s[128];
         // masking: key kv0 + i is visible iff i <= limit
@@ -974,7 +1099,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           // lazy rescale: only move the reference max when it grew by more than 2^kRescaleThreshold
           const bool need = (m_new - m) * c > kRescaleThreshold;   // (-inf -> finite) gives +inf -> true
           if (__any_sync(0xffffffffu, need)) {
-            if constexpr (T::kEarlyS) {
+            if constexpr (T::kEarlyS || T::kRotS) {
               // S_t(j) no longer implies that all of P_t(j-1) V has retired: wait for its second piece before touching O_t
               mbar_wait(bar_pv1 + 8 * t, (g - 1) & 1, TAG_PV1);
               tc_fence_after();
@@ -1038,7 +1163,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             if (tracer) FA_TRACE_AT(t, g, 3 + 2 * h);
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(bar_p + 16 * t + 8 * h);
+            mbar_arrive(bar_p_at(t, h, g));
             if (tracer) FA_TRACE_AT(t, g, 4 + 2 * h);
           }
         }

@@ -51,5 +51,7 @@ for name, bh, n, d, dt in SHAPES:
         extra = {"precise_ms": round(t_p, 4), "precise_max_abs_diff_vs_reference_kernel_scale1": float((o_p - o_ref).abs().max())}
     print(json.dumps({"config": name, "bh": bh, "n": n, "d": d, "dtype": str(dt).split(".")[-1], "ref_ms": round(t_ref, 3),
                       "ref_tflops": round(fl / t_ref * 1e-9, 2), "ours_ms": round(t_ours, 4), "ours_tflops": round(fl / t_ours * 1e-9, 1),
-                      "speedup": round(t_ref / t_ours, 1), "max_abs_diff_vs_reference_kernel_scale1": float((o - o_ref).abs().max()), **extra}), flush=True)
+                      "speedup": round(t_ref / t_ours, 1), "max_abs_diff_vs_reference_kernel_scale1": float((o - o_ref).abs().max()),
+                      # relative to the output's magnitude: a 16-bit O carries one ulp of its own format (bf16: 2^-8 relative, 0.031 at |O| in [4, 8))
+                      "max_rel_diff_vs_reference_kernel_scale1": float(((o - o_ref).abs() / o_ref.abs().clamp_min(1.0)).max()), **extra}), flush=True)
     del q, k, v, qq, kk, vv, o, o_ref
