@@ -52,7 +52,7 @@ def build_lib(force=False) -> Path:
 def build_harness(force=False):
     lib = build_lib(force)
     outs = []
-    for name, needs_lib in (("fa_check", True), ("test", True), ("umma_probe", False)):
+    for name, needs_lib in (("fa_check", True), ("test", True), ("umma_probe", False), ("mma_rate_probe", False)):
         src = HARNESS / f"{name}.cu"
         out = HARNESS / name
         deps = [src, CSRC / "ptx.cuh"] + ([lib] if needs_lib else [])

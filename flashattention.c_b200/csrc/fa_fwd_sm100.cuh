@@ -89,10 +89,15 @@
                              // -> columns [64, 128)) is issued right behind the first piece's P*V instead of after the second's
 #endif
 #ifndef FA_OPT_ROT_S
-#define FA_OPT_ROT_S 1       // two-slot instances with head dim <= 64: the S tiles of both slots rotate through THREE TMEM buffers
+#define FA_OPT_ROT_S 0       // 1: two-slot instances with head dim <= 64 rotate the S tiles of both slots through THREE TMEM buffers
                              // (3 * 128 + 2 * d <= 512 columns), so Q K^T of a slot's next step is issued a whole step early — behind
                              // the other slot's P V, into the buffer that P V has just freed — and drops out of the slot's serial
-                             // chain softmax(j) -> P V(j) -> Q K^T(j+1) -> softmax(j+1): softmax(j+1) starts when softmax(j) ends
+                             // chain softmax(j) -> P V(j) -> Q K^T(j+1) -> softmax(j+1).  Correct (161 GPU tests) and measured on B200
+                             // (profiles/r02_ab_rotating_s.log): fp32 d=32 3% faster, fp32 d=64 18-20% SLOWER, bf16 d=64 7% slower.
+                             // The chain is not what bounds these instances: their tensor work is instruction-rate bound (a
+                             // tcgen05.mma takes >= 47 cycles however small N is, harness/mma_rate_probe.cu: P V at d <= 64 is 16
+                             // such instructions per tile), the in-order issuer is busy for the whole step, and with S early both
+                             // slots' softmaxes run at the same time and share the MUFU instead of alternating with the MMAs.
 #endif
 #ifndef FA_OPT_ROLL_MMA
 #define FA_OPT_ROLL_MMA 0    // 1: the k-step loops of the MMA warp stay rolled (smaller code for a warp that shares its instruction
@@ -768,53 +773,74 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
       if (seq == 0) FA_TRACE_MISC(2, 1);
       if constexpr (T::kRotS) {
-        // ---- S tiles rotate through three buffers: see for_each_mma ----
+        // ---- S tiles rotate through three buffers (see for_each_mma, which the producer walks for the same tile order).
+        // Iteration n: P V of tile n = (slot n & 1, step n >> 1), then — in the same elect block, so the warp's work per step
+        // is what it is without the rotation — S of tile n + 3 into the buffer that P V has just finished with.
         bool ofree_done = false;
         int k_sh = 0, v_sh = 0;   // ring index of the K / V tile the two slots share (set by its first user)
-        for_each_mma<T::kSBufs>(w, [&](bool pv, int t, int j) {
-          const bool first_use = kv_first_use(w, t, j), last_use = kv_last_use(w, t, j);
-          if (first_use) {
-            if (pv) v_sh = ring++; else k_sh = ring++;
+        const int n_tiles = 2 * w.n_max;
+#pragma unroll 1
+        for (int n = -T::kSBufs; n < n_tiles; ++n) {
+          const int t = n & 1, j = n >> 1;
+          const int m = n + T::kSBufs, t2 = m & 1, j2 = m >> 1;
+          const bool has_pv = n >= 0 && j < w.n(t);
+          const bool has_s = m < n_tiles && j2 < w.n(t2);
+          if (!has_pv && !has_s) continue;
+          // ring tiles first used here (same order as the producer: V of the P V, then K of the S)
+          bool waited = false;
+          if (has_pv && kv_first_use(w, t, j)) {
+            v_sh = ring++;
+            wait_full(v_sh);
+            waited = true;
           }
-          const int idx = pv ? v_sh : k_sh;
-          const int buf = idx % T::kNBuf;
-          if (first_use) {
-            wait_full(idx);
-            tc_fence_after();
+          if (has_s && kv_first_use(w, t2, j2)) {
+            k_sh = ring++;
+            wait_full(k_sh);
+            waited = true;
           }
-          const uint32_t s_tile = tmem_base + T::kTmemS + static_cast<uint32_t>(((2 * j + t) % T::kSBufs) * kBlockN);
-          if (!pv) {
-            const int g = t == 0 ? gs_a++ : gs_b++;
-            if (elect_one_sync()) {
-              issue_s_at(s_tile, set * 2 + (w.split ? 0 : t), buf);
-              tc_commit(bar_s_at(t, g));
-              if (last_use) tc_commit(bar_empty + 8 * buf);
-            }
-            __syncwarp();
-          } else {
+          if (waited) tc_fence_after();
+          const int vbuf = v_sh % T::kNBuf, kbuf = k_sh % T::kNBuf;
+          const uint32_t s_new = tmem_base + T::kTmemS + static_cast<uint32_t>((m % T::kSBufs) * kBlockN);
+          const int gs = has_s ? (t2 == 0 ? gs_a++ : gs_b++) : 0;
+          auto issue_next_s = [&]() {   // inside an elect block
+            issue_s_at(s_new, set * 2 + (w.split ? 0 : t2), kbuf);
+            tc_commit(bar_s_at(t2, gs));
+            if (kv_last_use(w, t2, j2)) tc_commit(bar_empty + 8 * kbuf);
+          };
+          if (has_pv) {
             if (!ofree_done) {   // the first P V of an item overwrites O_t: the previous item's epilogues must have read it
               wait_ofree();
               ofree_done = true;
             }
             const int g = t == 0 ? gp_a++ : gp_b++;
+            const uint32_t s_tile = tmem_base + T::kTmemS + static_cast<uint32_t>((n % T::kSBufs) * kBlockN);
             const uint32_t o_acc = tmem_base + T::kTmemO + static_cast<uint32_t>(t * kHeadDim);
+            FA_TRACE_AT(2 + t, g, 0);
             if constexpr (T::kSplitP) {
               mbar_wait(bar_p_at(t, 0, g), par_at(g), TAG_P_FULL);
               tc_fence_after();
-              if (elect_one_sync()) issue_pv_at(o_acc, s_tile, buf, j > 0, 0, kKStepsSplit);
+              FA_TRACE_AT(2 + t, g, 1);
+              if (elect_one_sync()) issue_pv_at(o_acc, s_tile, vbuf, j > 0, 0, kKStepsSplit);
               __syncwarp();
+              FA_TRACE_AT(2 + t, g, 2);
             }
             mbar_wait(bar_p_at(t, 1, g), par_at(g), TAG_P_FULL);
             tc_fence_after();
+            FA_TRACE_AT(2 + t, g, 3);
             if (elect_one_sync()) {
-              issue_pv_at(o_acc, s_tile, buf, j > 0, T::kSplitP ? kKStepsSplit : 0, kKStepsPV);
+              issue_pv_at(o_acc, s_tile, vbuf, j > 0, T::kSplitP ? kKStepsSplit : 0, kKStepsPV);
               tc_commit(bar_pv1 + 8 * t);     // O_t holds all of step j (the softmax rescales O_t only behind this)
-              if (last_use) tc_commit(bar_empty + 8 * buf);
+              if (kv_last_use(w, t, j)) tc_commit(bar_empty + 8 * vbuf);
               if (j == w.n(t) - 1) tc_commit(bar_o + 8 * t);
+              if (has_s) issue_next_s();
             }
             __syncwarp();
+            FA_TRACE_AT(2 + t, g, 6);
+          } else {
+            if (elect_one_sync()) issue_next_s();
+            __syncwarp();
           }
-        });
+        }
       } else if (!w.split) {
         // ---- two Q tiles share every K/V tile: K_j then V_j in ring order ----
         const int r0 = ring;

@@ -1,0 +1,186 @@
+// mma_rate_probe.cu — how fast does one thread get tcgen05.mma through the tensor pipe, by operand source and shape?
+// One CTA, one issuing thread, R MMAs back to back into one accumulator, one commit, clock64 around it.
+//   SS: A and B from shared memory (K-major, SWIZZLE_128B: what S = Q K^T uses)      TS: A from tensor memory (what P V uses)
+// The question it answers: is kind::tf32 S = Q K^T (32-byte K-slices of 128-byte swizzled rows, both operands from SMEM)
+// bound by the operand fetch rather than by the pipe — and would Q as a TMEM operand lift that bound?
+#include <cstdio>
+#include <cstdlib>
+
+#include "../csrc/ptx.cuh"
+
+using namespace fa;
+
+template <bool kTF32, bool kFromTmem, int kN>
+__global__ void __launch_bounds__(128, 1) probe(long long* out, int reps, int inner) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + 4 * 16384, bar = base + 8 * 16384, tptr = bar + 16;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  // operands: small finite numbers
+  for (uint32_t i = threadIdx.x; i < 8 * 16384 / 4; i += blockDim.x) st_shared_b32(base + 4 * i, 0x3c003c00u);
+  fence_proxy_async_smem();
+  if (threadIdx.x < 32) {
+    tmem_alloc(tptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ld_shared_b32(tptr);
+  if (threadIdx.x == 0) {
+    constexpr uint32_t fmt = kTF32 ? 2u : 1u;
+    constexpr uint32_t idesc = make_idesc(fmt, 0, 128, kN);
+    constexpr uint64_t hi = make_sdesc_hi_sw128(16, 1024);
+    constexpr int kSteps = kTF32 ? 16 : 8;   // k-steps in a 128-row x (2 chunks of 128 B) operand tile, as in the kernel
+    long long best = 1ll << 60;
+    uint32_t parity = 0;
+    for (int r = 0; r < reps; ++r) {
+      const long long t0 = clock64();
+      for (int it = 0; it < inner; ++it) {
+#pragma unroll
+        for (int kk = 0; kk < kSteps; ++kk) {
+          const uint32_t off16 = ((kk >> 2) * 16384 + (kk & 3) * 32) >> 4;
+          if constexpr (kFromTmem) mma_ts<kTF32>(tmem, tmem + 256 + kk * 8, sdesc_at(hi, sB) + off16, idesc, 1u);
+          else mma_ss<kTF32>(tmem, sdesc_at(hi, sA) + off16, sdesc_at(hi, sB) + off16, idesc, 1u);
+        }
+      }
+      tc_commit(bar);
+      mbar_wait(bar, parity, 99);
+      parity ^= 1;
+      const long long dt = clock64() - t0;
+      best = dt < best ? dt : best;
+    }
+    out[0] = best;
+    out[1] = (long long)inner * kSteps;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
+// ---- the same with a CTA pair: one leader thread issues tcgen05.mma.cta_group::2 (M = 256: 128 rows in each CTA's tensor memory,
+// each CTA holds half of B's N extent in its shared memory), the commit is multicast to a barrier in both CTAs.
+FA_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+FA_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <bool kTF32, bool kFromTmem, int kN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe_pair(long long* out, int reps, int inner) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + 4 * 16384, bar = base + 8 * 16384, tptr = bar + 16;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  for (uint32_t i = threadIdx.x; i < 8 * 16384 / 4; i += blockDim.x) st_shared_b32(base + 4 * i, 0x3c003c00u);
+  fence_proxy_async_smem();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = ld_shared_b32(tptr);
+  if (threadIdx.x == 0) {
+    constexpr uint32_t fmt = kTF32 ? 2u : 1u;
+    constexpr uint32_t idesc = make_idesc(fmt, 0, 256, kN);
+    constexpr uint64_t hi = make_sdesc_hi_sw128(16, 1024);
+    constexpr int kSteps = kTF32 ? 16 : 8;
+    long long best = 1ll << 60;
+    uint32_t parity = 0;
+    for (int r = 0; r < reps; ++r) {
+      const long long t0 = clock64();
+      if (rank == 0) {
+        for (int it = 0; it < inner; ++it) {
+#pragma unroll
+          for (int kk = 0; kk < kSteps; ++kk) {
+            const uint32_t off16 = ((kk >> 2) * 16384 + (kk & 3) * 32) >> 4;
+            const uint64_t bd = sdesc_at(hi, sB) + off16, ad = sdesc_at(hi, sA) + off16;
+            const uint32_t at = tmem + 256 + kk * 8;
+            if constexpr (kFromTmem && kTF32)
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem), "r"(at), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+            else if constexpr (kFromTmem)
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem), "r"(at), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+            else if constexpr (kTF32)
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+            else
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                     "h"((uint16_t)3) : "memory");
+      }
+      mbar_wait(bar, parity, 98);
+      parity ^= 1;
+      const long long dt = clock64() - t0;
+      best = dt < best ? dt : best;
+    }
+    if (rank == 0) {
+      out[0] = best;
+      out[1] = (long long)inner * kSteps;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+template <bool kTF32, bool kFromTmem, int kN>
+void run_pair(const char* name) {
+  long long* d;
+  cudaMalloc(&d, 16);
+  cudaMemset(d, 0, 16);
+  auto k = probe_pair<kTF32, kFromTmem, kN>;
+  const int smem = 8 * 16384 + 1024 + 64;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  k<<<2, 128, smem>>>(d, 5, 8);
+  long long h[2] = {0, 0};
+  cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); exit(1); }
+  printf("{\"probe\": \"%s\", \"mmas\": %lld, \"cycles\": %lld, \"cycles_per_mma\": %.1f}\n", name, h[1], h[0], (double)h[0] / h[1]);
+  cudaFree(d);
+}
+
+template <bool kTF32, bool kFromTmem, int kN>
+void run(const char* name) {
+  long long* d;
+  cudaMalloc(&d, 16);
+  auto k = probe<kTF32, kFromTmem, kN>;
+  const int smem = 8 * 16384 + 1024 + 64;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  k<<<1, 128, smem>>>(d, 5, 8);
+  long long h[2] = {0, 0};
+  cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); exit(1); }
+  printf("{\"probe\": \"%s\", \"mmas\": %lld, \"cycles\": %lld, \"cycles_per_mma\": %.1f}\n", name, h[1], h[0], (double)h[0] / h[1]);
+  cudaFree(d);
+}
+
+int main() {
+  run<true, false, 128>("tf32 SS 128x128x8  (S = Q K^T as shipped)");
+  run<true, true, 128>("tf32 TS 128x128x8  (Q from TMEM)");
+  run<true, true, 64>("tf32 TS 128x64x8   (P V, d = 64)");
+  run<true, true, 32>("tf32 TS 128x32x8   (P V, d = 32)");
+  run<false, false, 128>("bf16 SS 128x128x16 (S = Q K^T, bf16)");
+  run<false, true, 128>("bf16 TS 128x128x16 (P V, d = 128)");
+  run<false, true, 64>("bf16 TS 128x64x16  (P V, d = 64)");
+  run_pair<true, false, 128>("pair tf32 SS 256x128x8  (S of two CTAs' Q tiles in one MMA)");
+  run_pair<true, true, 64>("pair tf32 TS 256x64x8   (P V, d = 64)");
+  run_pair<true, true, 32>("pair tf32 TS 256x32x8   (P V, d = 32)");
+  run_pair<false, false, 128>("pair bf16 SS 256x128x16");
+  run_pair<false, true, 128>("pair bf16 TS 256x128x16 (P V, d = 128)");
+  return 0;
+}
