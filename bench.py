@@ -543,7 +543,11 @@ def ring_c5(torch, dist, fab, rank, world, device, peaks, steps=3):
     # parity (2): 16 sampled rows per head against fp64 over all 131072 keys
     err_o, err_l = fp64_rows_check(torch, q, kf, vf, o, lse, scale, 16, 100 + rank)
     del o_one, lse_one, kf, vf
+    sampler = ClockSampler(torch.cuda.current_device())     # SM clock / power-cap state while all ranks run the ring
+    sampler.start()
     ms_ring = timed(lambda: fab.ring_attention(q, k, v, transport="p2p"), steps, 1)
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
     ms_nccl = timed(lambda: fab.ring_attention(q, k, v, transport="nccl"), max(1, steps - 1), 1)
 
     def local_only():   # the same kernels (merge fused in the epilogue) on the resident shard, no transfers
@@ -565,6 +569,7 @@ def ring_c5(torch, dist, fab, rank, world, device, peaks, steps=3):
             "ms_nccl_transport": round(ms_nccl, 3), "kernel_launches_per_forward": launches,
             "kv_bytes_pulled_per_gpu": 2 * k.numel() * 2 * (world - 1),
             "timing": f"CUDA events around one ring forward, barrier before each, mean of {steps}, max over ranks",
+            "clocks_during_ring_rank0": sampler.summary(),
             "parity": {"max_abs_diff_o_vs_one_kernel_over_full_sequence": d_o, "max_abs_diff_lse_vs_one_kernel": d_l,
                        "max_abs_err_o_vs_fp64_sampled_rows": err_o, "max_abs_err_lse_vs_fp64_sampled_rows": err_l, "rows_per_head": 16,
                        "tolerance_o": 2e-2, "ok": bool(d_o < 2e-2 and err_o < 2e-2 and err_l < 2e-3)}}
