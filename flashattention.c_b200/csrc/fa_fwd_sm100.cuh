@@ -189,6 +189,11 @@ struct FwdParams {
   const float* acc_o;
   const float* acc_lse;
   int head_dim;       // true head dim (<= the instance's): row pitch of O_acc
+  // Split-KV across CTAs (launches with far fewer Q tiles than SMs and many K/V tiles — decode-like shapes): the K/V tiles of
+  // every Q tile are cut into kv_splits runs of kv_chunk_tiles; split s is an item of its own that attends run s only and
+  // writes its normalised partial O (fp32) and LSE into slice s of a workspace shaped [kv_splits * batch, heads, n_q, d]
+  // (the O tensor map and `lse` describe that workspace); fa_combine_splits_kernel merges the slices.  1 = off.
+  int kv_splits, kv_chunk_tiles;
 };
 constexpr int kTraceSteps = 48;
 
@@ -278,6 +283,8 @@ struct Item {
   bool single, split;
   int n0, n1;              // K/V tiles of slot A / slot B (scalars: a runtime-indexed array would live in local memory)
   int kv_first1;           // first K/V tile of slot B (split mode), else 0
+  int kv_base;             // first K/V tile of the item (cross-CTA split-KV: run `kv_split` of the key sequence), else 0
+  int obatch;              // batch coordinate of the item's output rows: batch, or kv_split * batch_count + batch in the workspace
   int n_max;
   FA_DEVINL int n(int t) const { return t == 0 ? n0 : n1; }
   // Slot t gets a Q tile of its own in this item (in split mode slot B reads slot A's).  The ownership protocol of a Q buffer
@@ -297,8 +304,15 @@ FA_DEVINL Item decode_item(const FwdParams& p, int bid) {
   }
   int m_blk = bid % p.num_m_blocks;   // m fastest so neighbours share K/V in L2
   bid /= p.num_m_blocks;
+  int kv_split = 0;
+  if (p.kv_splits > 1) {
+    kv_split = bid % p.kv_splits;
+    bid /= p.kv_splits;
+  }
   it.head = bid % p.heads;
   it.batch = bid / p.heads;
+  it.kv_base = kv_split * p.kv_chunk_tiles;
+  it.obatch = kv_split * p.batch + it.batch;
   if (kCausal) m_blk = p.num_m_blocks - 1 - m_blk;  // heaviest blocks first
   it.row0 = m_blk * (2 * kBlockM) + half * kBlockM;
   it.split = it.single && p.tail_split != 0;   // slots A and B = two halves of the K/V range of ONE Q tile
@@ -311,6 +325,7 @@ FA_DEVINL Item decode_item(const FwdParams& p, int bid) {
       const int last_key = r0 + kBlockM - 1 + p.causal_offset;
       n = last_key < 0 ? 0 : min(n_kv_total, last_key / kBlockN + 1);
     }
+    if (p.kv_splits > 1) n = max(0, min(n - it.kv_base, p.kv_chunk_tiles));   // this run's share of the visible tiles
     if (r0 >= p.n_q || (it.single && t == 1)) n = 0;
     if (t == 0) it.n0 = n; else it.n1 = n;
   }
@@ -499,7 +514,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
           for (int c = 0; c < T::kDChunks; ++c)
             tma_load_4d(sKV + buf * T::kTileBytes + c * kChunkBytes, tm, bar_full + 8 * buf, c * T::kElemsPerChunk,
-                        kv_tile * kBlockN, w.head, w.batch);
+                        (w.kv_base + kv_tile) * kBlockN, w.head, w.batch);
         };
         // Q: one tile per slot; in split mode both slots read the same Q tile from slot A's buffer.  The buffer is
         // free once the epilogue that staged its O tile there (kQS items ago) has been read out by the TMA store.
@@ -1082,7 +1097,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const int set = seq % kQS;
       const int n_mine = w.n(t);
       const int q_row = (t == 0 ? w.row0 : w.row1) + r;
-      const int kv_first = t == 0 ? 0 : w.kv_first1;
+      const int kv_first = w.kv_base + (t == 0 ? 0 : w.kv_first1);
 
       float m = -INFINITY;  // running (possibly stale) row max, in raw q.k units
       float l = 0.f;        // running row sum of exp2((s - m) * c)
@@ -1255,7 +1270,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (p.acc_o != nullptr && stores) {
         float w_new = 1.f;
         if (q_row < p.n_q) {
-          const int64_t row_idx = (static_cast<int64_t>(w.batch) * p.heads + w.head) * p.n_q + q_row;
+          const int64_t row_idx = (static_cast<int64_t>(w.batch) * p.heads + w.head) * p.n_q + q_row;   // (never with kv_splits)
           acc_row = p.acc_o + row_idx * p.head_dim;
           const float la = p.acc_lse[row_idx], lb = lse_val;
           const float mx = fmaxf(la, lb);
@@ -1282,9 +1297,9 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (!stores) {
         if (zero_rows) {
           uint8_t* row = static_cast<uint8_t*>(p.o_ptr) +
-                         (static_cast<int64_t>(w.batch) * p.o_sb + static_cast<int64_t>(w.head) * p.o_sh + static_cast<int64_t>(q_row) * p.o_sn) * T::kOutSize;
+                         (static_cast<int64_t>(w.obatch) * p.o_sb + static_cast<int64_t>(w.head) * p.o_sh + static_cast<int64_t>(q_row) * p.o_sn) * T::kOutSize;
           for (int b = 0; b < p.o_row_bytes; b += 16) *reinterpret_cast<uint4*>(row + b) = make_uint4(0u, 0u, 0u, 0u);
-          if (p.lse != nullptr) p.lse[(static_cast<int64_t>(w.batch) * p.heads + w.head) * p.n_q + q_row] = -INFINITY;
+          if (p.lse != nullptr) p.lse[(static_cast<int64_t>(w.obatch) * p.heads + w.head) * p.n_q + q_row] = -INFINITY;
         }
       } else {
 #pragma unroll
@@ -1358,7 +1373,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
             for (int ch = 0; ch < T::kDChunks; ++ch)
               tma_store_4d(&tm_o, stage + ch * kChunkBytes, (round * T::kDChunks + ch) * kColsPerChunk, w.row0 + t * kBlockM,
-                           w.head, w.batch);
+                           w.head, w.obatch);
             tma_store_commit();
             if (kLateQFree && round + 1 == kRounds) {
               pend_qfree = set * 2 + t;
@@ -1372,7 +1387,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         // after the staging stores: a global store ahead of fence.proxy.async would make that fence wait for it
         if (p.lse != nullptr && q_row < p.n_q)
-          p.lse[(static_cast<int64_t>(w.batch) * p.heads + w.head) * p.n_q + q_row] = lse_val;
+          p.lse[(static_cast<int64_t>(w.obatch) * p.heads + w.head) * p.n_q + q_row] = lse_val;
       }
     }
     flush_qfree();

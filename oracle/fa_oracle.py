@@ -153,6 +153,22 @@ def ref_llmc_cpu(inp, B, T, C, NH):
     return out
 
 
+def ref_llmc_gpu_entry():
+    """The REFERENCE's own attention_forward6(out, inp, B, T, C, NH, block_size) (src/llm.c/attention_forward.cu:1106-1179:
+    permute -> flashattention kernel -> unpermute, device pointers) from oracle/_ref/libllmc_ref.so, as a ctypes function, or
+    None where the reference was not compiled.  Needs a GPU; it prints a timing line per call like the reference does."""
+    so = _HERE / "_ref" / "libllmc_ref.so"
+    if not so.exists():
+        return None
+    try:
+        fn = getattr(ctypes.CDLL(str(so)), "_Z18attention_forward6PfPKfiiiii")
+    except (OSError, AttributeError):
+        return None
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5
+    fn.restype = None
+    return fn
+
+
 def have_ref_torch_ext(d=64):
     return (_HERE / "_ref" / f"flash_ref_d{d}.so").exists()
 

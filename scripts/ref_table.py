@@ -55,3 +55,33 @@ for name, bh, n, d, dt in SHAPES:
                       # relative to the output's magnitude: a 16-bit O carries one ulp of its own format (bf16: 2^-8 relative, 0.031 at |O| in [4, 8))
                       "max_rel_diff_vs_reference_kernel_scale1": float(((o - o_ref).abs() / o_ref.abs().clamp_min(1.0)).max()), **extra}), flush=True)
     del q, k, v, qq, kk, vv, o, o_ref
+
+
+# ---- the llm.c surface: the reference's own attention_forward6 (permute -> flashattention -> unpermute, cudaMalloc/cudaFree and four
+# device synchronisations inside: src/llm.c/attention_forward.cu:1106-1179) vs the exported symbol of this repo, harness shape
+import contextlib
+import ctypes
+import os
+
+ref6 = fa_oracle.ref_llmc_gpu_entry()
+if ref6 is not None:
+    L = fab.lib()
+    L.attention_forward6.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 5
+    L.attention_forward6.restype = None
+    B, T, C, NH = 6, 4096, 768, 12
+    inp = torch.rand(B, T, 3 * C, device="cuda") * 2 - 1
+    o_ref, o_p, o_t = (torch.empty(B, T, C, device="cuda") for _ in range(3))
+    with open(os.devnull, "w") as devnull, contextlib.redirect_stdout(devnull):
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(devnull.fileno(), 1)       # the reference prints a timing line per call
+        try:
+            t_ref = timeit(lambda: ref6(o_ref.data_ptr(), inp.data_ptr(), B, T, C, NH, 256), 5)
+        finally:
+            os.dup2(saved, 1)
+    t_p = timeit(lambda: L.attention_forward6(o_p.data_ptr(), inp.data_ptr(), B, T, C, NH, 256), 10)
+    t_t = timeit(lambda: fab.attention_forward(6, o_t, inp, B, T, C, NH, 256, precise=False), 10)
+    print(json.dumps({"config": "llm.c harness shape B6 T4096 C768 NH12 (causal, packed QKV), attention_forward6", "ref_ms": round(t_ref, 3),
+                      "ours_precise_ms": round(t_p, 4), "ours_tf32_ms": round(t_t, 4), "speedup_precise": round(t_ref / t_p, 1),
+                      "max_abs_diff_precise_vs_reference_entry": float((o_p - o_ref).abs().max()),
+                      "max_abs_diff_tf32_vs_reference_entry": float((o_t - o_ref).abs().max())}), flush=True)

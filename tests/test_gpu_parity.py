@@ -777,6 +777,28 @@ def test_llmc_c_symbols_at_the_reference_gate(fab, oracle, cuda_device):
     assert err_fast < 1e-3
 
 
+def test_llmc_entry_vs_the_reference_llmc_entry(fab, oracle, cuda_device, capfd):
+    """The exported `attention_forward6` against the REFERENCE's own attention_forward6 (permute -> flashattention ->
+    unpermute, compiled from /root/reference into oracle/_ref/libllmc_ref.so) on the same device input: identical layout in
+    and out, results within the harness's 1e-4."""
+    ref6 = oracle.ref_llmc_gpu_entry()
+    if ref6 is None:
+        pytest.skip("oracle/_ref/libllmc_ref.so not built on this box")
+    L = fab.lib()
+    _llmc_argtypes(L)
+    B, T, C, NH = 2, 2048, 768, 12
+    d_inp = torch.rand(B, T, 3 * C, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(6)) * 2 - 1
+    out_ref = torch.full((B, T, C), float("nan"), device=cuda_device)
+    ref6(out_ref.data_ptr(), d_inp.data_ptr(), B, T, C, NH, 256)
+    torch.cuda.synchronize()
+    out = torch.full((B, T, C), float("nan"), device=cuda_device)
+    L.attention_forward6(out.data_ptr(), d_inp.data_ptr(), B, T, C, NH, 256)
+    err = float((out - out_ref).abs().max())
+    capfd.readouterr()      # the reference prints "Time taken ..." per call (src/llm.c/attention_forward.cu:1166)
+    print(f"attention_forward6 vs the reference's own: max abs diff {err:.3e}")
+    assert err <= 1e-4
+
+
 def test_run_flash_tiled_coarse_c_symbols_vs_oracle(fab, oracle, cuda_device):
     """Both torch-less launchers (test.cu:591-603; O, K, Q, V order; scale 1.0; d = 64) through ctypes against the
     tile-order restatement of the reference kernel."""
