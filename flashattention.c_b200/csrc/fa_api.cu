@@ -132,6 +132,42 @@ int next_work_counter(cudaStream_t st, unsigned int** out) {
   return FA_OK;
 }
 
+// ---- workspace of split-KV launches (partial O and LSE of every run).  Like the work counters it belongs to one (device, stream):
+// launches on a stream run one after the other and reuse it (grow-only), launches on different streams have their own.  A launch
+// that is being captured gets a stream-ordered allocation of its own instead (cudaMallocAsync / cudaFreeAsync become graph nodes):
+// a graph may be replayed on any stream.  (Outside capture cudaMallocAsync per call costs ~150 us with the default pool settings.)
+struct SplitWs { void* ptr = nullptr; size_t cap = 0; };
+std::unordered_map<cudaStream_t, SplitWs> g_split_ws[64];
+std::mutex g_split_ws_mu;
+
+int split_workspace(cudaStream_t st, size_t bytes, void** out, void** async_owned) {
+  *async_owned = nullptr;
+  int dev = 0;
+  FA_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return FA_ERR_NO_DEVICE;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  FA_CUDA(cudaStreamIsCapturing(st, &cap));
+  if (cap != cudaStreamCaptureStatusNone) {
+    FA_CUDA(cudaMallocAsync(out, bytes, st));
+    *async_owned = *out;
+    return FA_OK;
+  }
+  std::lock_guard<std::mutex> lk(g_split_ws_mu);
+  SplitWs& w = g_split_ws[dev][st];
+  if (w.cap < bytes) {
+    if (w.ptr) {
+      FA_CUDA(cudaStreamSynchronize(st));   // earlier launches on this stream may still be using the old buffer
+      cudaFree(w.ptr);
+      w.ptr = nullptr; w.cap = 0;
+    }
+    const size_t want = std::max(bytes + bytes / 2, (size_t)4 << 20);
+    FA_CUDA(cudaMalloc(&w.ptr, want));
+    w.cap = want;
+  }
+  *out = w.ptr;
+  return FA_OK;
+}
+
 // ---- cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -266,14 +302,47 @@ int run_tc(const fa_params* p, cudaStream_t st) {
   const bool bf16 = p->dtype != FA_F32;   // 16-bit operands (bf16 or fp16): kind::f16 instances
   const int in_dt = p->dtype;
   const int in_sz = bf16 ? 2 : 4;
-  const bool out_f32 = !bf16 || p->o_f32;
+  const bool precise = want_precise(p);
+  // ---- split-KV across CTAs (flash-decoding): a launch with far fewer 128-row Q tiles than SMs and a long key sequence cuts
+  // every Q tile's K/V tiles into `kv_splits` runs, one item each, and merges the runs' partials afterwards.  The reference
+  // sizes its grid by (batch, ceil(N / 32)) only (src/flashattention.cu:592) and leaves such launches on a handful of SMs.
+  // Off for accumulate mode and FA_FLAG_BATCH_INVARIANT (the split depends on the launch size); FA_B200_KV_SPLIT=0 / n: off / force.
+  int kv_splits = 1, kv_chunk_tiles = 0;
+  {
+    const int64_t kv_tiles = (p->n_k + fa::kBlockN - 1) / fa::kBlockN;
+    const int64_t q_tiles = p->batch * p->heads * ((p->n_q + fa::kBlockM - 1) / fa::kBlockM);
+    const int64_t sms = std::max(1, current_sm_count());
+    int64_t want = 1;
+    if (const char* e = getenv("FA_B200_KV_SPLIT")) want = std::max(1, atoi(e));
+    else if (2 * q_tiles <= sms && kv_tiles >= 8) want = std::min<int64_t>(std::min<int64_t>(sms / q_tiles, kv_tiles / 4), 64);
+    if (want > 1 && kv_tiles > 1 && !p->o_acc && !(p->flags & FA_FLAG_BATCH_INVARIANT)) {
+      kv_chunk_tiles = (int)((kv_tiles + want - 1) / want);
+      kv_splits = (int)((kv_tiles + kv_chunk_tiles - 1) / kv_chunk_tiles);
+      if (kv_splits <= 1) { kv_splits = 1; kv_chunk_tiles = 0; }
+    }
+  }
+  const bool out_f32 = !bf16 || p->o_f32 || kv_splits > 1;   // the runs' partials are fp32 whatever the caller's O is
   const int out_sz = out_f32 ? 4 : 2;
   CUtensorMap mq, mk, mv, mo;
-  int rc;
+  int rc = FA_OK;
+  // workspace of the runs' partials: O [kv_splits * batch, heads, n_q, d] fp32 + LSE [kv_splits * batch, heads, n_q], stream-ordered
+  float* ws_o = nullptr;
+  float* ws_lse = nullptr;
+  const int64_t ws_rows = p->batch * p->heads * p->n_q;
+  void* ws_async = nullptr;     // a stream-ordered allocation of this call (captured launches only), freed when run_tc returns
+  if (kv_splits > 1) {
+    void* ws = nullptr;
+    if ((rc = split_workspace(st, (size_t)kv_splits * ws_rows * (p->head_dim + 1) * sizeof(float), &ws, &ws_async))) return rc;
+    ws_o = static_cast<float*>(ws);
+    ws_lse = ws_o + (size_t)kv_splits * ws_rows * p->head_dim;
+  }
+  struct WsFree {
+    void* p; cudaStream_t st;
+    ~WsFree() { if (p) cudaFreeAsync(p, st); }
+  } ws_free{ws_async, st};
   // fp32 tensors are loaded through TFLOAT32 tensor maps: TMA rounds fp32 -> tf32 to nearest on the way into SMEM, which
   // removes the truncation bias the tensor core would otherwise apply (measured on B200: max error 4.1e-4 -> 9.8e-5 on C1).
   static const bool tf32_tma_env = [] { const char* e = getenv("FA_B200_TMA_TF32"); return !(e && atoi(e) == 0); }();
-  const bool precise = want_precise(p);
   const bool tf32_tma = tf32_tma_env && !precise;   // a precise instance needs the fp32 bits as they are (hi = trunc, lo = rest)
   if ((rc = make_map(&mq, p->q, in_sz, in_dt, p->batch, p->heads, p->n_q, p->head_dim, p->q_stride_b, p->q_stride_h, p->q_stride_n, CU_TENSOR_MAP_SWIZZLE_128B, tf32_tma))) return rc;
   if ((rc = make_map(&mk, p->k, in_sz, in_dt, p->batch, p->heads, p->n_k, p->head_dim, p->k_stride_b, p->k_stride_h, p->k_stride_n, CU_TENSOR_MAP_SWIZZLE_128B, tf32_tma))) return rc;
@@ -288,7 +357,10 @@ int run_tc(const fa_params* p, cudaStream_t st) {
     if (!bf16 && vv == 4) { v_layout = fa::kLayoutSw128; v_sbo = 1024; v_swz = CU_TENSOR_MAP_SWIZZLE_128B; }
   }
   if ((rc = make_map(&mv, p->v, in_sz, in_dt, p->batch, p->heads, p->n_k, p->head_dim, p->v_stride_b, p->v_stride_h, p->v_stride_n, v_swz, tf32_tma))) return rc;
-  if ((rc = make_map(&mo, p->o, out_sz, out_f32 ? (int)FA_F32 : in_dt, p->batch, p->heads, p->n_q, p->head_dim, p->o_stride_b, p->o_stride_h, p->o_stride_n))) return rc;
+  if (kv_splits > 1) {
+    const int64_t hd = p->head_dim;
+    if ((rc = make_map(&mo, ws_o, 4, (int)FA_F32, (int64_t)kv_splits * p->batch, p->heads, p->n_q, p->head_dim, p->heads * p->n_q * hd, p->n_q * hd, hd))) return rc;
+  } else if ((rc = make_map(&mo, p->o, out_sz, out_f32 ? (int)FA_F32 : in_dt, p->batch, p->heads, p->n_q, p->head_dim, p->o_stride_b, p->o_stride_h, p->o_stride_n))) return rc;
   fa::FwdParams fp;
   fp.scale = p->scale;
   fp.scale_log2 = p->scale * 1.4426950408889634f;
@@ -299,10 +371,16 @@ int run_tc(const fa_params* p, cudaStream_t st) {
   fp.o_ptr = p->o;
   fp.o_sb = p->o_stride_b; fp.o_sh = p->o_stride_h; fp.o_sn = p->o_stride_n;
   fp.o_row_bytes = p->head_dim * out_sz;
+  fp.kv_splits = kv_splits; fp.kv_chunk_tiles = kv_chunk_tiles;
+  if (kv_splits > 1) {
+    fp.lse = ws_lse;
+    fp.o_ptr = ws_o;
+    fp.o_sn = p->head_dim; fp.o_sh = p->n_q * (int64_t)p->head_dim; fp.o_sb = p->heads * fp.o_sh;
+  }
   fp.acc_o = p->o_acc; fp.acc_lse = p->lse_acc; fp.head_dim = p->head_dim;
   {
     // whole waves of 256-row CTAs; a remainder of at most SMs/2 blocks runs as twice as many 128-row CTAs (one wave)
-    const int64_t nb = (int64_t)fp.num_m_blocks * fp.heads * fp.batch;
+    const int64_t nb = (int64_t)fp.num_m_blocks * fp.heads * fp.batch * kv_splits;
     const int64_t sms = std::max(1, current_sm_count());
     int64_t n_big = (nb / sms) * sms;
     if (2 * (nb - n_big) > sms || getenv("FA_B200_NO_SPLIT_WAVE")) n_big = nb;
@@ -354,6 +432,7 @@ int run_tc(const fa_params* p, cudaStream_t st) {
   const bool c = p->causal != 0;
   const int di = tc_instance_dim(p);   // kernel instance (>= head_dim; the tensor maps carry the true head dim)
   const bool f16 = p->dtype == FA_F16;
+  auto launch = [&]() -> int {
   if (precise) {
     return c ? launch_tc<true, 64, true, false, false, true>(mq, mk, mv, mo, fp, st)
              : launch_tc<true, 64, false, false, false, true>(mq, mk, mv, mo, fp, st);
@@ -362,7 +441,7 @@ int run_tc(const fa_params* p, cudaStream_t st) {
     if (di == 32) return launch_tc_c<true, 32, false>(c, mq, mk, mv, mo, fp, st);
     if (di == 64) return launch_tc_c<true, 64, false>(c, mq, mk, mv, mo, fp, st);
     if (di == 128) return launch_tc_c<true, 128, false>(c, mq, mk, mv, mo, fp, st);
-  } else if (!p->o_f32) {
+  } else if (!out_f32) {
     if (di == 64) return f16 ? launch_tc_c<false, 64, false, true>(c, mq, mk, mv, mo, fp, st) : launch_tc_c<false, 64, false>(c, mq, mk, mv, mo, fp, st);
     if (di == 128) return f16 ? launch_tc_c<false, 128, false, true>(c, mq, mk, mv, mo, fp, st) : launch_tc_c<false, 128, false>(c, mq, mk, mv, mo, fp, st);
     if (di == 256) return f16 ? launch_tc_c<false, 256, false, true>(c, mq, mk, mv, mo, fp, st) : launch_tc_c<false, 256, false>(c, mq, mk, mv, mo, fp, st);
@@ -372,6 +451,26 @@ int run_tc(const fa_params* p, cudaStream_t st) {
     if (di == 256) return f16 ? launch_tc_c<false, 256, true, true>(c, mq, mk, mv, mo, fp, st) : launch_tc_c<false, 256, true>(c, mq, mk, mv, mo, fp, st);
   }
   return FA_ERR_UNSUPPORTED;
+  };
+  if ((rc = launch())) return rc;
+  if (kv_splits > 1) {
+    // merge the runs' partials into the caller's O (dtype, strides) and LSE
+    const unsigned grid = (unsigned)((ws_rows + 7) / 8);
+    const int H = (int)p->heads, nq = (int)p->n_q, hd = p->head_dim;
+    if (!bf16 || p->o_f32)
+      fa::fa_combine_splits_kernel<float><<<grid, 256, 0, st>>>(ws_o, ws_lse, kv_splits, ws_rows, H, nq, hd, static_cast<float*>(p->o),
+                                                                 p->o_stride_b, p->o_stride_h, p->o_stride_n, p->lse);
+    else if (f16)
+      fa::fa_combine_splits_kernel<__half><<<grid, 256, 0, st>>>(ws_o, ws_lse, kv_splits, ws_rows, H, nq, hd, static_cast<__half*>(p->o),
+                                                                  p->o_stride_b, p->o_stride_h, p->o_stride_n, p->lse);
+    else
+      fa::fa_combine_splits_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(ws_o, ws_lse, kv_splits, ws_rows, H, nq, hd,
+                                                                         static_cast<__nv_bfloat16*>(p->o), p->o_stride_b, p->o_stride_h,
+                                                                         p->o_stride_n, p->lse);
+    FA_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  return FA_OK;
 }
 
 template <typename TIn, typename TOut>

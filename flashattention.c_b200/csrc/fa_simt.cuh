@@ -159,6 +159,45 @@ __global__ void fa_merge_lse_kernel(float* __restrict__ lse_acc, const float* __
   lse_acc[row] = (mx == -INFINITY) ? -INFINITY : mx + logf(__expf(la - mx) + __expf(lb - mx));
 }
 
+// ---- split-KV across CTAs: merge the kv_splits normalised partials of every query row (workspace slices [s][b, h, i, :] fp32 and
+// their LSEs) into the caller's O (its dtype and strides) and LSE.  One warp per row; a run that saw no key has LSE = -inf.
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+fa_combine_splits_kernel(const float* __restrict__ o_ws, const float* __restrict__ lse_ws, int splits, int64_t rows, int heads, int n_q, int d,
+                         TOut* __restrict__ o, int64_t o_sb, int64_t o_sh, int64_t o_sn, float* __restrict__ lse) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float m = -INFINITY;
+  for (int s = 0; s < splits; ++s) m = fmaxf(m, lse_ws[s * rows + row]);
+  float denom = 0.f;
+  if (m != -INFINITY)
+    for (int s = 0; s < splits; ++s) denom += __expf(lse_ws[s * rows + row] - m);
+  const float inv = denom > 0.f ? 1.f / denom : 0.f;
+  float acc[kSimtMaxD / 32];
+#pragma unroll
+  for (int i = 0; i < kSimtMaxD / 32; ++i) acc[i] = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float ls = lse_ws[s * rows + row];
+    if (ls == -INFINITY) continue;
+    const float w = __expf(ls - m) * inv;
+    const float* src = o_ws + (s * rows + row) * d;
+#pragma unroll
+    for (int i = 0; i < kSimtMaxD / 32; ++i) {
+      const int col = lane + 32 * i;
+      if (col < d) acc[i] = fmaf(w, src[col], acc[i]);
+    }
+  }
+  const int64_t i_q = row % n_q, bh = row / n_q;
+  TOut* dst = o + (bh / heads) * o_sb + (bh % heads) * o_sh + i_q * o_sn;
+#pragma unroll
+  for (int i = 0; i < kSimtMaxD / 32; ++i) {
+    const int col = lane + 32 * i;
+    if (col < d) st_from_float(dst + col, acc[i]);
+  }
+  if (lse != nullptr && lane == 0) lse[row] = denom > 0.f ? m + logf(denom) : -INFINITY;
+}
+
 // fp32 -> bf16 / fp16 (final cast of the ring accumulator)
 template <typename T16>
 __global__ void fa_cast_16_kernel(const float* __restrict__ src, T16* __restrict__ dst, int64_t n) {

@@ -939,3 +939,57 @@ def test_accumulate_mode_causal_cross_length_and_masked_rows(fab, oracle, cuda_d
     assert o2.data_ptr() == o.data_ptr()
     assert tf32_err(o2[:, 256:].cpu().numpy(), o_ref[:, 256:]) < TOL_TF32_FEWKEYS
     assert tf32_err(o_lo.cpu().numpy(), o_ref[:, :256]) < TOL_TF32_FEWKEYS
+
+
+# ------------------------------------------------------------------ round 2: split-KV across CTAs (decode-like launches)
+@pytest.mark.parametrize("dtype,d,bh,nq,nk,causal", [(torch.float32, 64, 4, 128, 8192, False), (torch.float32, 64, 3, 100, 5000, True),
+                                                      (torch.bfloat16, 128, 8, 1, 16384, False), (torch.bfloat16, 128, 2, 300, 4096, True),
+                                                      (torch.float16, 64, 5, 64, 3000, False), (torch.float32, 32, 2, 256, 2048, False),
+                                                      (torch.float32, 128, 2, 17, 4096, False), (torch.bfloat16, 256, 1, 128, 4096, True)])
+def test_split_kv_across_ctas(fab, oracle, cuda_device, monkeypatch, dtype, d, bh, nq, nk, causal):
+    """Launches with far fewer Q tiles than SMs and a long key sequence (decode-like: the reference's grid of (batch, ceil(N/32))
+    CTAs, src/flashattention.cu:592, leaves them on a handful of SMs) cut every Q tile's K/V range into runs, one item each, and
+    merge the runs' partials in a second kernel.  Chosen automatically; must equal the oracle and the unsplit launch."""
+    q, k, v = seeded((bh, nq, d), 701), seeded((bh, nk, d), 702), seeded((bh, nk, d), 703)
+    if dtype != torch.float32:
+        q, k, v = (torch.from_numpy(x).to(dtype).float().numpy() for x in (q, k, v))
+    scale = 1 / math.sqrt(d)
+    o_ref, lse_ref = oracle.f64(q, k, v, scale, causal)
+    tol = TOL_BF16 if dtype != torch.float32 else TOL_TF32_FEWKEYS
+    outs = {}
+    for mode in ("auto", "0", "7"):
+        if mode == "auto":
+            monkeypatch.delenv("FA_B200_KV_SPLIT", raising=False)
+        else:
+            monkeypatch.setenv("FA_B200_KV_SPLIT", mode)
+        before = fab.launch_count()
+        o, lse = _run(fab, q, k, v, causal, scale, dtype=dtype)
+        assert fab.last_impl() == fab.FA_IMPL_TCGEN05
+        launches = fab.launch_count() - before
+        assert launches == (1 if mode == "0" else 2), (mode, launches)      # attention kernel (+ the combine kernel)
+        err = tf32_err(o, o_ref) if dtype == torch.float32 else np.abs(o - o_ref).max()
+        assert err < tol, (mode, err)
+        assert np.abs(lse - lse_ref).max() < 5e-3, mode
+        outs[mode] = o
+    assert np.abs(outs["auto"] - outs["0"]).max() < tol
+    # fp32-grade mode splits the same way
+    if dtype == torch.float32 and d <= 64:
+        monkeypatch.delenv("FA_B200_KV_SPLIT", raising=False)
+        tq, tk, tv = (torch.from_numpy(x).to(cuda_device) for x in (q, k, v))
+        o_p = fab.attention(tq, tk, tv, causal=causal, scale=scale, precise=True)
+        assert np.abs(o_p.cpu().numpy() - o_ref).max() < 2e-5
+
+
+def test_split_kv_is_off_for_batch_invariant_and_accumulate_calls(fab, cuda_device, monkeypatch):
+    monkeypatch.delenv("FA_B200_KV_SPLIT", raising=False)
+    q = torch.randn(2, 128, 64, device=cuda_device)
+    k, v = (torch.randn(2, 8192, 64, device=cuda_device) for _ in range(2))
+    for kwargs, want in (({}, 2), ({"batch_invariant": True}, 1)):
+        before = fab.launch_count()
+        fab.attention(q, k, v, **kwargs)
+        assert fab.launch_count() - before == want
+    o, lse = fab.attention(q, k[:, :4096], v[:, :4096], return_lse=True)
+    before = fab.launch_count()
+    o2 = fab.attention(q, k[:, 4096:], v[:, 4096:], acc=(o, lse))
+    assert fab.launch_count() - before == 1
+    assert float((o2 - fab.attention(q, k, v, batch_invariant=True)).abs().max()) < TOL_TF32
