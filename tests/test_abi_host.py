@@ -235,3 +235,56 @@ def test_ring_calls_cover_every_visible_pair_once_and_flag_the_last_call():
             for slot in (0, 1):
                 flags = [c[5] for c in calls if c[1] == slot]
                 assert flags[-1] and sum(flags) == 1
+
+
+def test_reference_bench_script_copy_is_pinned_byte_for_byte():
+    """tests/golden/bench_flashattention.py.sha256 pins the reference's own caller: the copy the GPU test runs from compat/
+    (oracle/_ref/, made by oracle/Makefile) and the reference's file where it is mounted must both hash to it."""
+    import hashlib
+
+    want = (ROOT / "tests" / "golden" / "bench_flashattention.py.sha256").read_text().strip()
+    seen = 0
+    for path in (Path("/root/reference/bench_flashattention.py"), ROOT / "oracle" / "_ref" / "bench_flashattention.py"):
+        if path.exists():
+            assert hashlib.sha256(path.read_bytes()).hexdigest() == want, path
+            seen += 1
+    if not seen:
+        pytest.skip("neither /root/reference nor oracle/_ref is present on this box")
+    # what the script's load(name='flash', sources=['src/main.cpp', 'src/flashattention.cu']) finds when run from compat/
+    for f in ("main.cpp", "flashattention.cu"):
+        assert (ROOT / "compat" / "src" / f).exists()
+    text = (ROOT / "compat" / "src" / "flashattention.cu").read_text()
+    assert "__global__" not in text and "dlopen" in text        # a host-only stub over the C-ABI, no kernel of its own
+
+
+def test_bench_host_helpers_without_a_gpu():
+    """bench.py's host-side helpers: core / NUMA binding never raises (it is an optimisation), and the fp64 sampled-row checker
+    (torch, used for the `parity` fields of the multi-GPU sections) agrees with the oracle."""
+    import importlib
+    import os
+
+    import numpy as np
+
+    sys.path.insert(0, str(ROOT))
+    bench = importlib.import_module("bench")
+    before = os.sched_getaffinity(0)
+    try:
+        for policy in ("off", "local", "spread"):
+            os.environ["FA_BENCH_NUMA"] = policy
+            info = bench.pin_to_gpu_numa(0, 2)
+            assert info["policy"] == policy
+    finally:
+        os.environ.pop("FA_BENCH_NUMA", None)
+        os.sched_setaffinity(0, before)
+    from oracle import fa_oracle
+
+    rng = np.random.default_rng(3)
+    q, k, v = (rng.standard_normal(s, dtype=np.float32) for s in ((1, 5, 40, 16), (1, 5, 96, 16), (1, 5, 96, 16)))
+    o_ref, lse_ref = fa_oracle.f64(q, k, v, 0.25, False)
+    o_bad = o_ref.copy()
+    o_bad[0, 3, 7, 2] += 0.5
+    tq, tk, tv = (torch.from_numpy(x) for x in (q, k, v))
+    err_o, err_l = bench.fp64_rows_check(torch, tq, tk, tv, torch.from_numpy(o_ref), torch.from_numpy(lse_ref), 0.25, 40, 1)
+    assert err_o < 1e-12 and err_l < 1e-12
+    err_o, _ = bench.fp64_rows_check(torch, tq, tk, tv, torch.from_numpy(o_bad), None, 0.25, 40, 1)
+    assert abs(err_o - 0.5) < 1e-9
