@@ -15,6 +15,7 @@
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "fa_fwd_sm100.cuh"
 #include "fa_simt.cuh"
@@ -138,6 +139,7 @@ int next_work_counter(cudaStream_t st, unsigned int** out) {
 // a graph may be replayed on any stream.  (Outside capture cudaMallocAsync per call costs ~150 us with the default pool settings.)
 struct SplitWs { void* ptr = nullptr; size_t cap = 0; };
 std::unordered_map<cudaStream_t, SplitWs> g_split_ws[64];
+std::vector<void*> g_split_ws_retired;
 std::mutex g_split_ws_mu;
 
 int split_workspace(cudaStream_t st, size_t bytes, void** out, void** async_owned) {
@@ -155,11 +157,10 @@ int split_workspace(cudaStream_t st, size_t bytes, void** out, void** async_owne
   std::lock_guard<std::mutex> lk(g_split_ws_mu);
   SplitWs& w = g_split_ws[dev][st];
   if (w.cap < bytes) {
-    if (w.ptr) {
-      FA_CUDA(cudaStreamSynchronize(st));   // earlier launches on this stream may still be using the old buffer
-      cudaFree(w.ptr);
-      w.ptr = nullptr; w.cap = 0;
-    }
+    // grow by 1.5x; the outgrown buffer is kept (a launch enqueued earlier on this stream may still be using it, and a
+    // synchronise-and-free here would stall the caller): growth is geometric, so what is retired stays below 2x what is live
+    if (w.ptr) g_split_ws_retired.push_back(w.ptr);
+    w.ptr = nullptr; w.cap = 0;
     const size_t want = std::max(bytes + bytes / 2, (size_t)4 << 20);
     FA_CUDA(cudaMalloc(&w.ptr, want));
     w.cap = want;
