@@ -993,3 +993,49 @@ def test_split_kv_is_off_for_batch_invariant_and_accumulate_calls(fab, cuda_devi
     o2 = fab.attention(q, k[:, 4096:], v[:, 4096:], acc=(o, lse))
     assert fab.launch_count() - before == 1
     assert float((o2 - fab.attention(q, k, v, batch_invariant=True)).abs().max()) < TOL_TF32
+
+
+@pytest.mark.parametrize("P,causal,zigzag", [(4, False, False), (3, True, False), (4, True, True), (2, True, True)])
+def test_fused_ring_steps_emulated_on_one_gpu(fab, oracle, cuda_device, P, causal, zigzag):
+    """The product path of the ring forward without the transport: every 'rank' walks ring.ring_calls — the list of its
+    attention calls with the accumulator each one folds into and the flag of the last one — through ring._Partials in fused
+    mode (accumulate-mode kernels, fp32 in place, last call writes bf16) on ONE GPU, on strided half-shard views when zig-zag.
+    The reassembled result must equal the unpartitioned forward; no merge or cast kernel may run."""
+    from flashattention_c_b200 import ring
+
+    B, H, d = 1, 2, 128
+    N = 256 * (2 * P if zigzag else P)
+    q, k, v = (_bf16_round(seeded((B, H, N, d), s)) for s in (131, 132, 133))
+    tq, tk, tv = (torch.from_numpy(x).cuda().to(torch.bfloat16) for x in (q, k, v))
+    scale = 1 / math.sqrt(d)
+    if zigzag:
+        shards = [[fab.zigzag_shard(t, r, P).contiguous() for t in (tq, tk, tv)] for r in range(P)]
+    else:
+        n = N // P
+        shards = [[t[:, :, r * n:(r + 1) * n].contiguous() for t in (tq, tk, tv)] for r in range(P)]
+    c = shards[0][0].shape[-2] // 2
+    outs, lses = [], []
+    launches0 = fab.launch_count()
+    n_calls = 0
+    for r in range(P):
+        parts = ring._Partials(None, None, scale)          # fused: the kernels merge in their epilogues
+        for src, slot, hq, keys, cz, is_last in ring.ring_calls(r, P, causal, zigzag):
+            q_ = shards[r][0] if hq is None else shards[r][0][..., hq * c:(hq + 1) * c, :]
+            k_s, v_s = shards[src][1], shards[src][2]
+            if keys == "lo":
+                k_s, v_s = k_s[..., :c, :], v_s[..., :c, :]
+            parts.step(slot, q_, k_s, v_s, cz, is_last)
+            n_calls += 1
+        o_r, lse_r = parts.result(zigzag)
+        assert o_r.dtype == torch.bfloat16
+        outs.append(o_r)
+        lses.append(lse_r)
+    assert fab.launch_count() - launches0 == n_calls          # one attention kernel per call, nothing else
+    if zigzag:
+        o = fab.zigzag_unshard(outs, P)
+        lse = fab.zigzag_unshard([l.unsqueeze(-1) for l in lses], P).squeeze(-1)
+    else:
+        o, lse = torch.cat(outs, dim=-2), torch.cat(lses, dim=-1)
+    o_ref, lse_ref = oracle.f64(q, k, v, scale, causal)
+    assert np.abs(o.float().cpu().numpy() - o_ref).max() < TOL_BF16
+    assert np.abs(lse.cpu().numpy() - lse_ref).max() < 1e-3
