@@ -99,6 +99,14 @@
                              // such instructions per tile), the in-order issuer is busy for the whole step, and with S early both
                              // slots' softmaxes run at the same time and share the MUFU instead of alternating with the MMAs.
 #endif
+// K/V ring depth of the 128- and 256-byte-row instances (what fits next to the Q tiles: 2 x 2 x 16 KB + 8 x 16 KB, 2 x 32 KB + 5 x 32 KB).
+// The MMA warp waits ~500 cycles per step for tiles that were requested 1 - 1.5 steps earlier (profiles/r02_ab_ring_depth.log).
+#ifndef FA_NBUF_NARROW
+#define FA_NBUF_NARROW 8
+#endif
+#ifndef FA_NBUF_MID
+#define FA_NBUF_MID 5
+#endif
 #ifndef FA_OPT_ROLL_MMA
 #define FA_OPT_ROLL_MMA 0    // 1: the k-step loops of the MMA warp stay rolled (smaller code for a warp that shares its instruction
                              // cache with the unrolled exp loops of the softmax warps)
@@ -233,7 +241,7 @@ struct FwdTraits {
   // never builds 256-row or split-KV items for them) and slot B's warps idle.  K_(j+1) then streams in under the softmax of step j and
   // V_(j+1) under Q K^T(j+1) and that softmax — the tensor pipe has nothing else to do for a lone Q tile anyway.
   static constexpr int kSlots = kTileChunks <= 2 ? 2 : 1;
-  static constexpr int kNBuf = kTileChunks == 1 ? 8 : (kTileChunks == 2 ? 5 : 2);   // K/V ring depth (tiles)
+  static constexpr int kNBuf = kTileChunks == 1 ? FA_NBUF_NARROW : (kTileChunks == 2 ? FA_NBUF_MID : 2);   // K/V ring depth (tiles)
   static constexpr int kUmmaK = 32 / kInSize;                  // K per tcgen05.mma: 8 (tf32) / 16 (bf16)
   static constexpr int kQSets = kTileChunks == 1 ? 2 : 1;      // Q double-buffered across items where SMEM allows
   static constexpr bool kComp = kTF32 && !kPrecise && (FA_OPT_TF32_COMP != 0);   // tf32 truncation compensated instead of reproduced
