@@ -116,26 +116,41 @@ class _P2PState:
     def __init__(self, like, group):
         import ctypes
 
-        from ._lib import check, lib
+        from ._lib import FaError, check, lib
 
         self.L, self.check = lib(), check
         self.group, self.dev = group, like.device
         self.half = like.numel() * like.element_size()     # bytes of K (= bytes of V)
         world, rank = dist.get_world_size(group), dist.get_rank(group)
+        self.local, self.peer = None, []
+
+        def agree(ok, what):
+            """Every rank learns whether the step worked everywhere, so that a failure on one rank (no CUDA IPC in this
+            container, out of memory, ...) is an exception on all of them and not a hang in the next collective."""
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                self.unmap_peers()
+                self.free_local()
+                raise FaError(f"ring p2p transport unavailable: {what} failed on at least one rank (use transport='nccl')")
+
         ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
-        check(self.L.fa_p2p_alloc(2 * self.half, ctypes.byref(ptr), handle), "fa_p2p_alloc")
-        self.local = ptr.value
+        rc = self.L.fa_p2p_alloc(2 * self.half, ctypes.byref(ptr), handle)
+        if rc == 0:
+            self.local = ptr.value
+        agree(rc == 0, "fa_p2p_alloc")
         mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=self.dev)
         handles = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(handles, mine, group=group)
-        self.peer = []
+        ok = True
         for r in range(world):
             if r == rank:
                 self.peer.append(self.local)
             else:
                 pp = ctypes.c_void_p()
-                check(self.L.fa_p2p_open(bytes(handles[r].cpu().tolist()), ctypes.byref(pp)), f"fa_p2p_open (rank {r})")
+                ok = ok and self.L.fa_p2p_open(bytes(handles[r].cpu().tolist()), ctypes.byref(pp)) == 0
                 self.peer.append(pp.value)
+        agree(ok, "fa_p2p_open")
         self.side = torch.cuda.Stream(device=self.dev)
         self.flag = torch.zeros(1, device=self.dev)
         # staging ping-pong [2][K | V], shaped like the caller's shards
