@@ -6,6 +6,8 @@ Host-side mirror of the reference interface (names, argument meaning, error beha
   attention(Q, K, V, causal, scale, ...)         the same operator with an explicit scale (default 1/sqrt(d)) and LSE
   attention_forward(kernel_num, out, inp, ...)   src/llm.c/attention_forward.cu:1183-1211 (packed QKV, causal, 1/sqrt(hs))
   load_extension()                               the pybind module (`.forward(Q,K,V,causal)`) bench_flashattention.py:10,70 expects
+  attention_autograd(Q, K, V, causal, scale)     the forward kernel with gradients (backward: blockwise recomputation from the saved LSE
+                                                 with torch matmuls — plumbing, not a kernel of this repository; the reference is forward only)
 
 Everything runs on hand-written sm_100a kernels through the C-ABI library libfa_b200.so
 (include/fa_b200.h).  There is no CPU or eager-PyTorch fallback: without the library or a B200 the calls raise.
@@ -22,6 +24,7 @@ from .api import (  # noqa: F401
     load_extension,
     merge_partials,
 )
+from .autograd import attention_autograd  # noqa: F401
 from .ring import bh_shard_range, ring_attention, ring_p2p_release, sharded_attention, zigzag_shard, zigzag_step_plan, zigzag_unshard  # noqa: F401
 
 __version__ = "0.1.0"

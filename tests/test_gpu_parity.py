@@ -1039,3 +1039,31 @@ def test_fused_ring_steps_emulated_on_one_gpu(fab, oracle, cuda_device, P, causa
     o_ref, lse_ref = oracle.f64(q, k, v, scale, causal)
     assert np.abs(o.float().cpu().numpy() - o_ref).max() < TOL_BF16
     assert np.abs(lse.cpu().numpy() - lse_ref).max() < 1e-3
+
+
+# ------------------------------------------------------------------ round 2: gradients (generality)
+@pytest.mark.parametrize("dtype,d,nq,nk,causal", [(torch.float32, 64, 300, 300, False), (torch.float32, 64, 257, 257, True),
+                                                  (torch.bfloat16, 128, 384, 384, True), (torch.float32, 32, 100, 260, True),
+                                                  (torch.bfloat16, 64, 200, 128, False)])
+def test_autograd_backward_vs_torch_autograd(fab, cuda_device, dtype, d, nq, nk, causal):
+    """attention_autograd: forward on the tcgen05 kernel, backward recomputed blockwise from the saved LSE.  dQ, dK, dV against
+    torch.autograd through a float64 softmax(scale * Q K^T + mask) V on the same (rounded) inputs."""
+    g = torch.Generator(device="cpu").manual_seed(d + nq)
+    q, k, v = (torch.randn(3, n, d, generator=g).to(dtype).to(cuda_device).requires_grad_(True) for n in (nq, nk, nk))
+    d_o = torch.randn(3, nq, d, generator=g).to(dtype).to(cuda_device)
+    scale = 1 / math.sqrt(d)
+    o = fab.attention_autograd(q, k, v, causal=causal, scale=scale, precise=dtype == torch.float32)
+    o.backward(d_o)
+    q64, k64, v64 = (t.detach().double().requires_grad_(True) for t in (q, k, v))
+    s = (q64 @ k64.transpose(1, 2)) * scale
+    if causal:
+        i, j = torch.arange(nq, device=cuda_device)[:, None], torch.arange(nk, device=cuda_device)[None, :]
+        s = s.masked_fill(j > i + (nk - nq), float("-inf"))
+    o64 = torch.softmax(s, dim=-1) @ v64
+    o64.backward(d_o.double())
+    tol = 3e-2 if dtype == torch.bfloat16 else 2e-3
+    assert float((o.detach().double() - o64.detach()).abs().max()) < (TOL_BF16 if dtype == torch.bfloat16 else 1e-4)
+    for name, got, want in (("dq", q.grad, q64.grad), ("dk", k.grad, k64.grad), ("dv", v.grad, v64.grad)):
+        err = float((got.double() - want).abs().max())
+        ref = float(want.abs().max())
+        assert err < tol * max(1.0, ref), (name, err, ref)
