@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <torch/types.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
