@@ -1067,3 +1067,53 @@ def test_autograd_backward_vs_torch_autograd(fab, cuda_device, dtype, d, nq, nk,
         err = float((got.double() - want).abs().max())
         ref = float(want.abs().max())
         assert err < tol * max(1.0, ref), (name, err, ref)
+
+
+# ------------------------------------------------------------------ round 2: randomised shapes
+@pytest.mark.parametrize("seed", [20261017, 7, 99])
+def test_randomised_shapes_vs_cuda_core_kernel(fab, cuda_device, monkeypatch, seed):
+    """3 x 120 seeded random problems — (batch*heads, n_q, n_k, head dim, dtype, causal, flags, split-KV setting), sized so that every
+    scheduling regime shows up (one item, a partial wave, several items per CTA, dead slots, rows without keys, split-KV across CTAs,
+    one-slot and precise instances) — tcgen05 kernel against the independent CUDA-core kernel on the whole tensor, O and LSE."""
+    rng = np.random.default_rng(seed)
+    dims = {torch.float32: [8, 16, 32, 40, 64, 96, 128], torch.bfloat16: [16, 64, 80, 128, 192, 256], torch.float16: [32, 64, 128]}
+    worst = {}
+    for case in range(120):
+        dtype = [torch.float32, torch.bfloat16, torch.float16][int(rng.integers(0, 3))]
+        d = int(rng.choice(dims[dtype]))
+        regime = int(rng.integers(0, 4))
+        if regime == 0:      # many items per CTA, ragged
+            bh, nq = int(rng.integers(100, 260)), int(rng.integers(129, 900))
+            nk = nq if rng.random() < 0.6 else int(rng.integers(1, 1200))
+        elif regime == 1:    # decode-like
+            bh, nq, nk = int(rng.integers(1, 24)), int(rng.integers(1, 260)), int(rng.integers(1024, 6000))
+        elif regime == 2:    # tiny
+            bh, nq, nk = int(rng.integers(1, 6)), int(rng.integers(1, 300)), int(rng.integers(1, 300))
+        else:                # partial wave
+            bh, nq = int(rng.integers(8, 80)), int(rng.integers(200, 1400))
+            nk = nq
+        causal = bool(rng.integers(0, 2))
+        precise = dtype == torch.float32 and d <= 64 and rng.random() < 0.3
+        batch_invariant = rng.random() < 0.2
+        split = rng.choice(["auto", "0", "3"])
+        if split == "auto":
+            monkeypatch.delenv("FA_B200_KV_SPLIT", raising=False)
+        else:
+            monkeypatch.setenv("FA_B200_KV_SPLIT", str(split))
+        g = torch.Generator(device=cuda_device).manual_seed(case)
+        q = torch.randn(bh, nq, d, device=cuda_device, generator=g).to(dtype)
+        k, v = (torch.randn(bh, nk, d, device=cuda_device, generator=g).to(dtype) for _ in range(2))
+        scale = 1 / math.sqrt(d)
+        o, lse = fab.attention(q, k, v, causal=causal, scale=scale, return_lse=True, precise=precise, batch_invariant=batch_invariant)
+        assert fab.last_impl() == fab.FA_IMPL_TCGEN05
+        o_s, lse_s = fab.attention(q, k, v, causal=causal, scale=scale, return_lse=True, impl=fab.FA_IMPL_SIMT)
+        err = float(((o.float() - o_s.float()).abs() / (1 + o_s.float().abs())).max())
+        both_inf = torch.isneginf(lse) & torch.isneginf(lse_s)
+        err_l = float(torch.where(both_inf, torch.zeros_like(lse), (lse - lse_s).abs()).max())
+        tol = 2e-5 if precise else (3 * TOL_TF32_FEWKEYS if dtype == torch.float32 else TOL_BF16)
+        key = (str(dtype).split(".")[-1], precise)
+        worst[key] = max(worst.get(key, 0.0), err)
+        what = (case, dtype, d, bh, nq, nk, causal, precise, batch_invariant, split)
+        assert err < tol, (what, err)
+        assert err_l < (1e-4 if precise else 5e-3) and not bool(torch.isnan(o.float()).any()), (what, err_l)
+    print("worst |o - o_simt| / (1 + |o_simt|) per path:", {k_: f"{v_:.2e}" for k_, v_ in worst.items()})
