@@ -385,7 +385,7 @@ def run_ours(args, torch, dist, rank, world, device):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/); None = not captured
-TRAFFIC_BYTES = {"C2": 117.4e6, "C4": 1057.8e6}   # dram__bytes_read+write per launch, profiles/r01_ncu_summary.md (v9 kernel)
+TRAFFIC_BYTES = {"C1": 12.66e6, "C2": 116.4e6, "C3": 52.6e6, "C4": 1058.5e6}   # dram__bytes_read+write per launch, profiles/r02_ncu_summary.md (kernel v10)
 
 
 def other_configs(torch, fab, device, flush, peaks):
@@ -429,6 +429,17 @@ def other_configs(torch, fab, device, flush, peaks):
     ms = min(time_kernel(torch, lambda: fab.attention(q, k, v, out=out), 2, 1, flush))
     res["C5_one_gpu"] = {"ms": round(ms, 3), "tflops": round(flops_of(1, Hh, Nn, dd) / ms * 1e-9, 1),
                          "frac_tensor_peak_sustained": round(flops_of(1, Hh, Nn, dd) / ms * 1e-9 / peaks["bf16_sustained"], 4)}
+    del q, k, v, out
+    # the HBM-bound end of the operator: a decode-like launch (one query row per head, 131072 keys), split over the K/V axis
+    # across CTAs and merged by the combine kernel; algorithmic bytes = K and V read once
+    q = torch.randn(32, 1, 128, device=device).to(torch.bfloat16)
+    k, v = (torch.randn(32, 131072, 128, device=device).to(torch.bfloat16) for _ in range(2))
+    out = torch.empty_like(q)
+    ms = sorted(time_kernel(torch, lambda: fab.attention(q, k, v, out=out), 10, 3, flush))[5]
+    kv_bytes = 2.0 * k.numel() * 2
+    res["decode_bh32_nq1_nk131072_bf16_d128"] = {"ms": round(ms, 5), "kv_gbs": round(kv_bytes / ms * 1e-6, 1),
+                                                 "frac_hbm_peak": round(kv_bytes / ms * 1e-6 / peaks["hbm"], 4),
+                                                 "note": "split-KV across CTAs + fa_combine_splits_kernel (2 launches); bytes = K + V read once"}
     del q, k, v, out
     return res
 
