@@ -35,6 +35,7 @@ class FaParams(ctypes.Structure):
         ("o_stride_b", ctypes.c_int64), ("o_stride_h", ctypes.c_int64), ("o_stride_n", ctypes.c_int64),
         ("impl", ctypes.c_int32), ("flags", ctypes.c_int32),
         ("o_acc", ctypes.c_void_p), ("lse_acc", ctypes.c_void_p),
+        ("kv_heads", ctypes.c_int64),
     ]
 
 

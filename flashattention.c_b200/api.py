@@ -29,6 +29,9 @@ def _stream_ptr(device) -> int:
 
 
 def _shape4(Q, K, V):
+    """-> (batch, heads, n_q, n_k, d, kv_heads).  K and V may have fewer heads than Q (grouped-query / multi-query attention,
+    heads % kv_heads == 0) in the 4-D form [B, H_kv, N, d]; a 3-D [B*H, N, d] tensor carries no batch / head split, so K and V
+    then need as many slices as Q."""
     if Q.dim() not in (3, 4) or K.dim() != Q.dim() or V.dim() != Q.dim():
         raise FaError("expected Q, K, V as [B*H, N, d] or [B, H, N, d]")
     if not (Q.is_cuda and K.is_cuda and V.is_cuda):
@@ -37,15 +40,16 @@ def _shape4(Q, K, V):
         raise FaError("Q, K, V dtype mismatch")
     if Q.dim() == 3:
         b, h, nq, d = 1, Q.shape[0], Q.shape[1], Q.shape[2]
-        nk = K.shape[1]
-        ok = K.shape[0] == h and V.shape[0] == h and V.shape[1] == nk and K.shape[2] == d and V.shape[2] == d
+        nk, hk = K.shape[1], K.shape[0]
+        ok = hk == h and V.shape[0] == h and V.shape[1] == nk and K.shape[2] == d and V.shape[2] == d
     else:
         b, h, nq, d = Q.shape
-        nk = K.shape[2]
-        ok = K.shape[:2] == Q.shape[:2] and V.shape[:2] == Q.shape[:2] and V.shape[2] == nk and K.shape[3] == d and V.shape[3] == d
+        nk, hk = K.shape[2], K.shape[1]
+        ok = (K.shape[0] == b and V.shape[0] == b and V.shape[1] == hk and hk > 0 and h % hk == 0 and V.shape[2] == nk
+              and K.shape[3] == d and V.shape[3] == d)
     if not ok:
         raise FaError(f"shape mismatch: Q {tuple(Q.shape)} K {tuple(K.shape)} V {tuple(V.shape)}")
-    return b, h, nq, nk, d
+    return b, h, nq, nk, d, hk
 
 
 def _tma_view(t: torch.Tensor) -> torch.Tensor:
@@ -71,7 +75,8 @@ def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False
     """O = softmax(scale * Q K^T [+ causal mask]) V.   scale defaults to 1/sqrt(d).
 
     Q, K, V: CUDA tensors [B*H, N, d] or [B, H, N, d], float32, bfloat16 or float16; strided views with a contiguous last axis
-    (e.g. a slice of the sequence axis) are read in place.
+    (e.g. a slice of the sequence axis) are read in place.  4-D K and V may have fewer heads than Q (grouped-query / multi-query
+    attention: [B, H_kv, N, d] with H % H_kv == 0; query head h reads K/V head h // (H / H_kv)).
     Returns O (same shape/dtype as Q; float32 if out_f32) and, if return_lse, LSE float32 [..., N].
     batch_invariant: FA_FLAG_BATCH_INVARIANT — a (batch, head) slice gives bit-identical results whatever else is in the
     launch (alone, in a larger batch, on another rank of a B x H sharded job); costs the split-KV tail optimisation.
@@ -82,7 +87,7 @@ def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False
     With a float32 result (float32 inputs, or out_f32) and no `out`, O_acc is updated in place and returned; LSE_acc is always
     updated in place (and returned if return_lse).  This is one step of the ring forward (ring.py).
     """
-    b, h, nq, nk, d = _shape4(Q, K, V)
+    b, h, nq, nk, d, hk = _shape4(Q, K, V)
     Q, K, V = _tma_view(Q), _tma_view(K), _tma_view(V)
     if scale is None:
         scale = 1.0 / math.sqrt(d)
@@ -118,6 +123,7 @@ def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False
         p.flags = (_lib.FA_FLAG_BATCH_INVARIANT if batch_invariant else 0) | (_lib.FA_FLAG_PRECISE if precise else 0)
         if acc is not None:
             p.o_acc, p.lse_acc = acc[0].data_ptr(), acc[1].data_ptr()
+        p.kv_heads = hk if hk != h else 0
         check(lib().fa_forward_ex(ctypes.byref(p), ctypes.c_void_p(_stream_ptr(Q.device))), "fa_forward_ex")
     return (O, lse) if return_lse else O
 

@@ -64,6 +64,8 @@ class _Attention(torch.autograd.Function):
 def attention_autograd(Q, K, V, causal=False, scale=None, precise=False):
     """`attention` with gradients: O = softmax(scale * Q K^T [+ causal mask]) V through the tcgen05 forward kernel, backward by
     blockwise recomputation from the saved LSE (module docstring).  Q, K, V: CUDA tensors [B*H, N, d] or [B, H, N, d]."""
+    if K.shape[:-2] != Q.shape[:-2] or V.shape != K.shape:
+        raise api.FaError("attention_autograd needs K and V with Q's batch and head counts (expand grouped K/V heads first)")
     if scale is None:
         scale = 1.0 / math.sqrt(Q.shape[-1])
     return _Attention.apply(Q, K, V, bool(causal), float(scale), bool(precise))

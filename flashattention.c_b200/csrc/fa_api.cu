@@ -346,7 +346,8 @@ int run_tc(const fa_params* p, cudaStream_t st) {
   static const bool tf32_tma_env = [] { const char* e = getenv("FA_B200_TMA_TF32"); return !(e && atoi(e) == 0); }();
   const bool tf32_tma = tf32_tma_env && !precise;   // a precise instance needs the fp32 bits as they are (hi = trunc, lo = rest)
   if ((rc = make_map(&mq, p->q, in_sz, in_dt, p->batch, p->heads, p->n_q, p->head_dim, p->q_stride_b, p->q_stride_h, p->q_stride_n, CU_TENSOR_MAP_SWIZZLE_128B, tf32_tma))) return rc;
-  if ((rc = make_map(&mk, p->k, in_sz, in_dt, p->batch, p->heads, p->n_k, p->head_dim, p->k_stride_b, p->k_stride_h, p->k_stride_n, CU_TENSOR_MAP_SWIZZLE_128B, tf32_tma))) return rc;
+  const int64_t kv_heads = p->kv_heads > 0 ? p->kv_heads : p->heads;
+  if ((rc = make_map(&mk, p->k, in_sz, in_dt, p->batch, kv_heads, p->n_k, p->head_dim, p->k_stride_b, p->k_stride_h, p->k_stride_n, CU_TENSOR_MAP_SWIZZLE_128B, tf32_tma))) return rc;
   // V is the MN-major B operand of P*V: bf16 uses the ordinary 128B swizzle; 32-bit (tf32) MN-major operands must
   // be in the SWIZZLE_128B_BASE32B layout (32-byte units over 4-row groups), written by TMA's 128B_ATOM_32B mode.
   uint32_t v_lbo = fa::kChunkBytes, v_sbo = bf16 ? 1024 : 512, v_layout = bf16 ? fa::kLayoutSw128 : fa::kLayoutSw128Base32;
@@ -357,7 +358,7 @@ int run_tc(const fa_params* p, cudaStream_t st) {
     if (!bf16 && vv == 3) { v_lbo = 512; v_sbo = fa::kChunkBytes; }
     if (!bf16 && vv == 4) { v_layout = fa::kLayoutSw128; v_sbo = 1024; v_swz = CU_TENSOR_MAP_SWIZZLE_128B; }
   }
-  if ((rc = make_map(&mv, p->v, in_sz, in_dt, p->batch, p->heads, p->n_k, p->head_dim, p->v_stride_b, p->v_stride_h, p->v_stride_n, v_swz, tf32_tma))) return rc;
+  if ((rc = make_map(&mv, p->v, in_sz, in_dt, p->batch, kv_heads, p->n_k, p->head_dim, p->v_stride_b, p->v_stride_h, p->v_stride_n, v_swz, tf32_tma))) return rc;
   if (kv_splits > 1) {
     const int64_t hd = p->head_dim;
     if ((rc = make_map(&mo, ws_o, 4, (int)FA_F32, (int64_t)kv_splits * p->batch, p->heads, p->n_q, p->head_dim, p->heads * p->n_q * hd, p->n_q * hd, hd))) return rc;
@@ -373,6 +374,7 @@ int run_tc(const fa_params* p, cudaStream_t st) {
   fp.o_sb = p->o_stride_b; fp.o_sh = p->o_stride_h; fp.o_sn = p->o_stride_n;
   fp.o_row_bytes = p->head_dim * out_sz;
   fp.kv_splits = kv_splits; fp.kv_chunk_tiles = kv_chunk_tiles;
+  fp.kv_group = (int)(p->heads / kv_heads);
   if (kv_splits > 1) {
     fp.lse = ws_lse;
     fp.o_ptr = ws_o;
@@ -497,6 +499,7 @@ int run_simt(const fa_params* p, cudaStream_t st) {
   sp.o_sb = p->o_stride_b; sp.o_sh = p->o_stride_h; sp.o_sn = p->o_stride_n;
   sp.n_q = (int)p->n_q; sp.n_k = (int)p->n_k; sp.heads = (int)p->heads; sp.batch = (int)p->batch; sp.head_dim = p->head_dim;
   sp.causal = p->causal; sp.causal_offset = (int)(p->n_k - p->n_q); sp.scale = p->scale;
+  sp.kv_group = (int)(p->heads / (p->kv_heads > 0 ? p->kv_heads : p->heads));
   if (p->dtype == FA_F32) return launch_simt<float, float>(sp, st);
   if (p->dtype == FA_F16) return p->o_f32 ? launch_simt<__half, float>(sp, st) : launch_simt<__half, __half>(sp, st);
   if (p->o_f32) return launch_simt<__nv_bfloat16, float>(sp, st);
@@ -572,6 +575,7 @@ int fa_forward_ex(const fa_params* p, void* stream) {
   if (p->n_q > 0x7fffffff || p->n_k > 0x7fffffff || p->batch > 0x7fffffff || p->heads > 0x7fffffff) return FA_ERR_INVALID_ARG;
   if (p->o_f32 && p->dtype == FA_F32) return FA_ERR_INVALID_ARG;   // fp32 inputs already give fp32 O
   if ((p->o_acc == nullptr) != (p->lse_acc == nullptr)) return FA_ERR_INVALID_ARG;
+  if (p->kv_heads < 0 || (p->kv_heads > 0 && (p->kv_heads > p->heads || p->heads % p->kv_heads != 0))) return FA_ERR_INVALID_ARG;
   if (p->o_acc && ((reinterpret_cast<uintptr_t>(p->o_acc) & 15) || p->head_dim % 4)) return FA_ERR_ALIGNMENT;
   int major = 0;
   int rc = probe_device(&major);

@@ -202,6 +202,7 @@ struct FwdParams {
   // writes its normalised partial O (fp32) and LSE into slice s of a workspace shaped [kv_splits * batch, heads, n_q, d]
   // (the O tensor map and `lse` describe that workspace); fa_combine_splits_kernel merges the slices.  1 = off.
   int kv_splits, kv_chunk_tiles;
+  int kv_group;       // query heads per K/V head (grouped-query / multi-query attention): K/V head of query head h is h / kv_group; 1 = MHA
 };
 constexpr int kTraceSteps = 48;
 
@@ -522,7 +523,7 @@ fa_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
           for (int c = 0; c < T::kDChunks; ++c)
             tma_load_4d(sKV + buf * T::kTileBytes + c * kChunkBytes, tm, bar_full + 8 * buf, c * T::kElemsPerChunk,
-                        (w.kv_base + kv_tile) * kBlockN, w.head, w.batch);
+                        (w.kv_base + kv_tile) * kBlockN, w.head / p.kv_group, w.batch);
         };
         // Q: one tile per slot; in split mode both slots read the same Q tile from slot A's buffer.  The buffer is
         // free once the epilogue that staged its O tile there (kQS items ago) has been read out by the TMA store.

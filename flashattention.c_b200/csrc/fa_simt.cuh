@@ -20,6 +20,7 @@ struct SimtParams {
   const void* q; const void* k; const void* v; void* o; float* lse;
   int64_t q_sb, q_sh, q_sn, k_sb, k_sh, k_sn, v_sb, v_sh, v_sn, o_sb, o_sh, o_sn;  // element strides
   int n_q, n_k, heads, batch, head_dim;
+  int kv_group;   // query heads per K/V head (1 = every query head has its own)
   int causal, causal_offset;
   float scale;
 };
@@ -51,8 +52,8 @@ fa_fwd_simt_kernel(const SimtParams p) {
   const int row = blockIdx.x * kSimtRows + warp;
   const bool row_ok = row < p.n_q;
   const TIn* q = static_cast<const TIn*>(p.q) + b * p.q_sb + h * p.q_sh;
-  const TIn* k = static_cast<const TIn*>(p.k) + b * p.k_sb + h * p.k_sh;
-  const TIn* v = static_cast<const TIn*>(p.v) + b * p.v_sb + h * p.v_sh;
+  const TIn* k = static_cast<const TIn*>(p.k) + b * p.k_sb + (h / p.kv_group) * p.k_sh;
+  const TIn* v = static_cast<const TIn*>(p.v) + b * p.v_sb + (h / p.kv_group) * p.v_sh;
 
   for (int i = lane; i < d; i += 32) sQ[warp * d + i] = row_ok ? ld_as_float(q + (int64_t)row * p.q_sn + i) : 0.f;
 

@@ -90,6 +90,10 @@ typedef struct fa_params {
    * ring-forward step: the merge costs no launch and no extra pass over O, and the last step can write 16-bit O directly. */
   const float* o_acc;
   const float* lse_acc;
+  /* Grouped-query / multi-query attention: K and V have kv_heads heads ([batch, kv_heads, n_k, head_dim], their own strides) and
+   * query head h reads K/V head h / (heads / kv_heads).  0 (or == heads) = one K/V head per query head.  heads % kv_heads == 0.
+   * The K/V tiles of a group are fetched once per query head but by neighbouring items, so they are shared in L2. */
+  int64_t kv_heads;
 } fa_params;
 
 /*

@@ -1117,3 +1117,55 @@ def test_randomised_shapes_vs_cuda_core_kernel(fab, cuda_device, monkeypatch, se
         assert err < tol, (what, err)
         assert err_l < (1e-4 if precise else 5e-3) and not bool(torch.isnan(o.float()).any()), (what, err_l)
     print("worst |o - o_simt| / (1 + |o_simt|) per path:", {k_: f"{v_:.2e}" for k_, v_ in worst.items()})
+
+
+# ------------------------------------------------------------------ round 2: grouped-query / multi-query K and V
+@pytest.mark.parametrize("dtype,d,h,hk,nq,nk,causal", [(torch.float32, 64, 8, 2, 300, 300, True), (torch.bfloat16, 128, 32, 8, 512, 512, False),
+                                                        (torch.bfloat16, 128, 16, 1, 1, 4096, False), (torch.float32, 32, 6, 3, 700, 700, True),
+                                                        (torch.float16, 64, 12, 4, 200, 1000, True), (torch.float32, 128, 4, 2, 260, 260, False)])
+def test_grouped_query_heads(fab, oracle, cuda_device, dtype, d, h, hk, nq, nk, causal):
+    """K and V with fewer heads than Q (fa_params.kv_heads): query head h reads K/V head h // (H / H_kv) through the same tensor
+    maps, no expanded copy.  Against the oracle on explicitly repeated K/V, on both kernel families, and (fp32, d <= 64) in the
+    fp32-grade mode; the decode-like case also goes through the split over the K/V axis."""
+    B = 2
+    q = seeded((B, h, nq, d), 801)
+    k, v = seeded((B, hk, nk, d), 802), seeded((B, hk, nk, d), 803)
+    if dtype != torch.float32:
+        q, k, v = (torch.from_numpy(x).to(dtype).float().numpy() for x in (q, k, v))
+    scale = 1 / math.sqrt(d)
+    rep = h // hk
+    o_ref, lse_ref = oracle.f64(q, np.repeat(k, rep, axis=1), np.repeat(v, rep, axis=1), scale, causal)
+    tq, tk, tv = (torch.from_numpy(x).to(cuda_device).to(dtype) for x in (q, k, v))
+    o, lse = fab.attention(tq, tk, tv, causal=causal, scale=scale, return_lse=True)
+    assert fab.last_impl() == fab.FA_IMPL_TCGEN05
+    err = tf32_err(o.float().cpu().numpy(), o_ref) if dtype == torch.float32 else float(np.abs(o.float().cpu().numpy() - o_ref).max())
+    assert err < (TOL_TF32_FEWKEYS if dtype == torch.float32 else TOL_BF16)
+    assert np.abs(lse.cpu().numpy() - lse_ref).max() < 5e-3
+    if d % 8 == 0:
+        o_s = fab.attention(tq, tk, tv, causal=causal, scale=scale, impl=fab.FA_IMPL_SIMT)
+        assert float((o.float() - o_s.float()).abs().max()) < (3 * TOL_TF32_FEWKEYS if dtype == torch.float32 else TOL_BF16)
+    if dtype == torch.float32 and d <= 64:
+        o_p = fab.attention(tq, tk, tv, causal=causal, scale=scale, precise=True)
+        assert np.abs(o_p.cpu().numpy() - o_ref).max() < 2e-5
+    # same bits as the expanded copy
+    o_e = fab.attention(tq, tk.repeat_interleave(rep, dim=1), tv.repeat_interleave(rep, dim=1), causal=causal, scale=scale,
+                        batch_invariant=True)
+    assert torch.equal(o_e, fab.attention(tq, tk, tv, causal=causal, scale=scale, batch_invariant=True))
+
+
+def test_grouped_query_argument_checks(fab, cuda_device):
+    import ctypes
+
+    from flashattention_c_b200 import _lib
+
+    q = torch.randn(1, 6, 128, 64, device=cuda_device)
+    k = torch.randn(1, 4, 128, 64, device=cuda_device)
+    with pytest.raises(fab.FaError):
+        fab.attention(q, k, k)                       # 6 query heads over 4 K/V heads
+    p = _lib.FaParams()
+    out = torch.empty_like(q)
+    p.q, p.k, p.v, p.o = q.data_ptr(), k.data_ptr(), k.data_ptr(), out.data_ptr()
+    p.batch, p.heads, p.n_q, p.n_k, p.head_dim, p.dtype, p.scale, p.kv_heads = 1, 6, 128, 128, 64, _lib.FA_F32, 0.125, 4
+    for name in ("q", "k", "v", "o"):
+        setattr(p, f"{name}_stride_n", 64), setattr(p, f"{name}_stride_h", 128 * 64), setattr(p, f"{name}_stride_b", 6 * 128 * 64)
+    assert fab.lib().fa_forward_ex(ctypes.byref(p), None) == -1
