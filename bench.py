@@ -421,15 +421,6 @@ def other_configs(torch, fab, device, flush, peaks):
         ms = sorted(time_kernel(torch, lambda: fab.attention_forward(6, outl, inp, Bl, Tl, Cl, NHl, 256, precise=prec), 10, 3, flush))[5]
         res[label] = {"ms": round(ms, 5), "tflops_causal": round(fl_l / ms * 1e-9, 1)}
     del inp, outl
-    # config 5 on ONE GPU: the whole 131072-long sequence in one launch (the ring's single-GPU baseline)
-    Hh, Nn, dd = 32, 131072, 128
-    g = torch.Generator(device=device).manual_seed(5)
-    q, k, v = (torch.randn(1, Hh, Nn, dd, device=device, generator=g).to(torch.bfloat16) for _ in range(3))
-    out = torch.empty_like(q)
-    ms = min(time_kernel(torch, lambda: fab.attention(q, k, v, out=out), 2, 1, flush))
-    res["C5_one_gpu"] = {"ms": round(ms, 3), "tflops": round(flops_of(1, Hh, Nn, dd) / ms * 1e-9, 1),
-                         "frac_tensor_peak_sustained": round(flops_of(1, Hh, Nn, dd) / ms * 1e-9 / peaks["bf16_sustained"], 4)}
-    del q, k, v, out
     # the HBM-bound end of the operator: a decode-like launch (one query row per head, 131072 keys), split over the K/V axis
     # across CTAs and merged by the combine kernel; algorithmic bytes = K and V read once
     q = torch.randn(32, 1, 128, device=device).to(torch.bfloat16)
@@ -440,6 +431,15 @@ def other_configs(torch, fab, device, flush, peaks):
     res["decode_bh32_nq1_nk131072_bf16_d128"] = {"ms": round(ms, 5), "kv_gbs": round(kv_bytes / ms * 1e-6, 1),
                                                  "frac_hbm_peak": round(kv_bytes / ms * 1e-6 / peaks["hbm"], 4),
                                                  "note": "split-KV across CTAs + fa_combine_splits_kernel (2 launches); bytes = K + V read once"}
+    del q, k, v, out
+    # config 5 on ONE GPU: the whole 131072-long sequence in one launch (the ring's single-GPU baseline)
+    Hh, Nn, dd = 32, 131072, 128
+    g = torch.Generator(device=device).manual_seed(5)
+    q, k, v = (torch.randn(1, Hh, Nn, dd, device=device, generator=g).to(torch.bfloat16) for _ in range(3))
+    out = torch.empty_like(q)
+    ms = min(time_kernel(torch, lambda: fab.attention(q, k, v, out=out), 2, 1, flush))
+    res["C5_one_gpu"] = {"ms": round(ms, 3), "tflops": round(flops_of(1, Hh, Nn, dd) / ms * 1e-9, 1),
+                         "frac_tensor_peak_sustained": round(flops_of(1, Hh, Nn, dd) / ms * 1e-9 / peaks["bf16_sustained"], 4)}
     del q, k, v, out
     return res
 
