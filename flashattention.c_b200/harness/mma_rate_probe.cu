@@ -61,6 +61,96 @@ __global__ void __launch_bounds__(128, 1) probe(long long* out, int reps, int in
   if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
 }
 
+// ---- tensor-memory contention: the same MMA stream while `busy_warps` other warps of the CTA stream tcgen05.ld / tcgen05.st
+// over other TMEM columns (what the softmax warps do).  Does concurrent softmax traffic slow the MMAs down?
+template <bool kTF32, bool kFromTmem, int kN>
+__global__ void __launch_bounds__(288, 1) probe_contended(long long* out, int reps, int inner, int busy_warps) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + 4 * 16384, bar = base + 8 * 16384, tptr = bar + 16, flag = bar + 32;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    st_shared_b32(flag, 1u);
+    fence_mbar_init();
+  }
+  for (uint32_t i = threadIdx.x; i < 8 * 16384 / 4; i += blockDim.x) st_shared_b32(base + 4 * i, 0x3c003c00u);
+  fence_proxy_async_smem();
+  if (warp == 8) {
+    tmem_alloc(tptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ld_shared_b32(tptr);
+  if (warp < 8) {
+    if (warp < busy_warps) {
+      // lanes 32 * (warp % 4) .. + 31, columns [256, 384) (warps 0-3) or [384, 512) (warps 4-7): away from the MMA's D and A columns
+      const uint32_t t = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 256 + (warp >> 2) * 128;
+      uint32_t r[32];
+      for (int spin = 0; spin < 200000 && ld_shared_b32(flag) != 0u; ++spin) {   // bounded: a probe must never hang the GPU
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          tmem_ld32(t + q * 32, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] += 1u;
+          tmem_st32(t + q * 32, r);
+        }
+        tc_wait_st();
+      }
+    }
+  } else if (threadIdx.x == 256) {
+    constexpr uint32_t fmt = kTF32 ? 2u : 1u;
+    constexpr uint32_t idesc = make_idesc(fmt, 0, 128, kN);
+    constexpr uint64_t hi = make_sdesc_hi_sw128(16, 1024);
+    constexpr int kSteps = kTF32 ? 16 : 8;
+    long long best = 1ll << 60;
+    uint32_t parity = 0;
+    for (int r = 0; r < reps; ++r) {
+      const long long t0 = clock64();
+      for (int it = 0; it < inner; ++it) {
+#pragma unroll
+        for (int kk = 0; kk < kSteps; ++kk) {
+          const uint32_t off16 = ((kk >> 2) * 16384 + (kk & 3) * 32) >> 4;
+          if constexpr (kFromTmem) mma_ts<kTF32>(tmem, tmem + 128 + kk * 8, sdesc_at(hi, sB) + off16, idesc, 1u);
+          else mma_ss<kTF32>(tmem, sdesc_at(hi, sA) + off16, sdesc_at(hi, sB) + off16, idesc, 1u);
+        }
+      }
+      tc_commit(bar);
+      mbar_wait(bar, parity, 97);
+      parity ^= 1;
+      const long long dt = clock64() - t0;
+      best = dt < best ? dt : best;
+    }
+    out[0] = best;
+    out[1] = (long long)inner * kSteps;
+    st_shared_b32(flag, 0u);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+template <bool kTF32, bool kFromTmem, int kN>
+void run_contended(const char* name, int busy_warps) {
+  long long* d;
+  cudaMalloc(&d, 16);
+  cudaMemset(d, 0, 16);
+  auto k = probe_contended<kTF32, kFromTmem, kN>;
+  const int smem = 8 * 16384 + 1024 + 64;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  k<<<1, 288, smem>>>(d, 5, 8, busy_warps);
+  long long h[2] = {0, 0};
+  cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); exit(1); }
+  printf("{\"probe\": \"%s, %d warps streaming tcgen05.ld/st\", \"mmas\": %lld, \"cycles\": %lld, \"cycles_per_mma\": %.1f}\n", name, busy_warps, h[1],
+         h[0], (double)h[0] / h[1]);
+  fflush(stdout);
+  cudaFree(d);
+}
+
 // ---- the same with a CTA pair: one leader thread issues tcgen05.mma.cta_group::2 (M = 256: 128 rows in each CTA's tensor memory,
 // each CTA holds half of B's N extent in its shared memory), the commit is multicast to a barrier in both CTAs.
 FA_DEVINL uint32_t cluster_ctarank() {
@@ -151,6 +241,7 @@ void run_pair(const char* name) {
   cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); exit(1); }
   printf("{\"probe\": \"%s\", \"mmas\": %lld, \"cycles\": %lld, \"cycles_per_mma\": %.1f}\n", name, h[1], h[0], (double)h[0] / h[1]);
+  fflush(stdout);
   cudaFree(d);
 }
 
@@ -166,6 +257,7 @@ void run(const char* name) {
   cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) { printf("%s: %s\n", name, cudaGetErrorString(e)); exit(1); }
   printf("{\"probe\": \"%s\", \"mmas\": %lld, \"cycles\": %lld, \"cycles_per_mma\": %.1f}\n", name, h[1], h[0], (double)h[0] / h[1]);
+  fflush(stdout);
   cudaFree(d);
 }
 
@@ -177,6 +269,10 @@ int main() {
   run<false, false, 128>("bf16 SS 128x128x16 (S = Q K^T, bf16)");
   run<false, true, 128>("bf16 TS 128x128x16 (P V, d = 128)");
   run<false, true, 64>("bf16 TS 128x64x16  (P V, d = 64)");
+  for (int w : {0, 4, 8}) run_contended<true, false, 128>("tf32 SS 128x128x8", w);
+  for (int w : {0, 4, 8}) run_contended<true, true, 64>("tf32 TS 128x64x8", w);
+  for (int w : {0, 4, 8}) run_contended<false, false, 128>("bf16 SS 128x128x16", w);
+  for (int w : {0, 4, 8}) run_contended<false, true, 128>("bf16 TS 128x128x16", w);
   run_pair<true, false, 128>("pair tf32 SS 256x128x8  (S of two CTAs' Q tiles in one MMA)");
   run_pair<true, true, 64>("pair tf32 TS 256x64x8   (P V, d = 64)");
   run_pair<true, true, 32>("pair tf32 TS 256x32x8   (P V, d = 32)");
