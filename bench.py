@@ -552,6 +552,17 @@ def ring_c5(torch, dist, fab, rank, world, device, peaks, steps=3):
         transport_note = f"p2p unavailable ({str(e)[:120]}): NCCL send/recv rotation"
     else:
         transport_note = "p2p (copy-engine pulls from CUDA-IPC-mapped peer buffers over NVLink)"
+    def timed_local(f, reps):     # no collective inside: for work only one rank does
+        tot = 0.0
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            f()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / reps
+
     launches0 = fab.launch_count()
     o, lse = fab.ring_attention(q, k, v, transport=transport)
     launches = fab.launch_count() - launches0
@@ -561,7 +572,22 @@ def ring_c5(torch, dist, fab, rank, world, device, peaks, steps=3):
     d_l = float((lse - lse_one).abs().max())
     # parity (2): 16 sampled rows per head against fp64 over all 131072 keys
     err_o, err_l = fp64_rows_check(torch, q, kf, vf, o, lse, scale, 16, 100 + rank)
-    del o_one, lse_one, kf, vf
+    del o_one, lse_one
+    # the same problem on ONE GPU (one launch over the whole sequence), twice: with every GPU of the box running it at the same
+    # time (the box's power / clock state is then that of the ring run) and on rank 0 alone with the others idle
+    qf = torch.cat([q] * world, dim=2)[:, :, :N]          # a full-length query tensor (the values do not matter for timing)
+    out_full = torch.empty_like(qf)
+
+    def one_gpu():
+        fab.attention(qf, kf, vf, scale=scale, out=out_full)
+
+    ms_one_busy = timed(one_gpu, 1, 1)
+    ms_one_alone = 0.0
+    dist.barrier()
+    if rank == 0:
+        ms_one_alone = timed_local(one_gpu, 1)
+    dist.barrier()
+    del qf, out_full, kf, vf
     sampler = ClockSampler(torch.cuda.current_device())     # SM clock / power-cap state while all ranks run the ring
     sampler.start()
     ms_ring = timed(lambda: fab.ring_attention(q, k, v, transport=transport), steps, 1)
@@ -575,9 +601,9 @@ def ring_c5(torch, dist, fab, rank, world, device, peaks, steps=3):
             acc[0] = fab.attention(q, k, v, scale=scale, out_f32=s_ < world - 1, acc=(acc[0], acc[1]))
 
     ms_local = timed(local_only, steps, 1)
-    t = torch.tensor([ms_ring, ms_nccl, ms_local, d_o, d_l, err_o, err_l], dtype=torch.float64, device=device)
+    t = torch.tensor([ms_ring, ms_nccl, ms_local, d_o, d_l, err_o, err_l, ms_one_busy, ms_one_alone], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_ring, ms_nccl, ms_local, d_o, d_l, err_o, err_l = t.tolist()
+    ms_ring, ms_nccl, ms_local, d_o, d_l, err_o, err_l, ms_one_busy, ms_one_alone = t.tolist()
     fl = 4.0 * H * float(N) * N * d
     per_gpu = fl / world / ms_ring * 1e-9
     return {"workload": f"C5: B=1 H={H} d={d} N={N} bf16 non-causal, sequence cut into {world} shards of {n_loc}",
@@ -585,6 +611,8 @@ def ring_c5(torch, dist, fab, rank, world, device, peaks, steps=3):
             "ms": round(ms_ring, 3), "tflops_total": round(fl / ms_ring * 1e-9, 1), "tflops_per_gpu": round(per_gpu, 1),
             "frac_sustained_peak": round(per_gpu / peaks["bf16_sustained"], 4), "frac_burst_peak": round(per_gpu / peaks["bf16"], 4),
             "ms_same_kernels_no_transfers": round(ms_local, 3), "overlap": round(ms_local / ms_ring, 4),
+            "ms_one_gpu_same_run_all_gpus_busy": round(ms_one_busy, 3), "speedup_vs_one_gpu_all_busy": round(ms_one_busy / ms_ring, 3),
+            "ms_one_gpu_same_run_alone": round(ms_one_alone, 3), "speedup_vs_one_gpu_alone": round(ms_one_alone / ms_ring, 3),
             "ms_nccl_transport": round(ms_nccl, 3), "kernel_launches_per_forward": launches,
             "kv_bytes_pulled_per_gpu": 2 * k.numel() * 2 * (world - 1),
             "timing": f"CUDA events around one ring forward, barrier before each, mean of {steps}, max over ranks",
