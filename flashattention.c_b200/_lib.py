@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = [
     "fa_strerror", "fa_last_cuda_error", "fa_last_impl", "fa_version", "fa_launch_count",
     "fa_watchdog_info",
     "fa_p2p_alloc", "fa_p2p_open", "fa_p2p_close", "fa_p2p_free", "fa_copy_async", "fa_query_instance",
+    "fa_backward",
 ]
 
 
@@ -37,6 +38,15 @@ class FaParams(ctypes.Structure):
         ("o_acc", ctypes.c_void_p), ("lse_acc", ctypes.c_void_p),
         ("kv_heads", ctypes.c_int64),
     ]
+
+
+class FaBwdParams(ctypes.Structure):
+    _fields_ = (
+        [(n, ctypes.c_void_p) for n in ("q", "k", "v", "o", "d_o", "lse", "dq", "dk", "dv")]
+        + [(n, ctypes.c_int64) for n in ("batch", "heads", "kv_heads", "n_q", "n_k")]
+        + [("head_dim", ctypes.c_int32), ("dtype", ctypes.c_int32), ("causal", ctypes.c_int32), ("scale", ctypes.c_float)]
+        + [(f"{t}_stride_{a}", ctypes.c_int64) for t in ("q", "k", "v", "o", "do", "dq", "dk", "dv") for a in ("b", "h", "n")]
+    )
 
 
 class FaError(RuntimeError):
@@ -60,6 +70,8 @@ def lib() -> ctypes.CDLL:
         L.fa_forward.restype = ctypes.c_int
         L.fa_forward_ex.argtypes = [ctypes.POINTER(FaParams), vp]
         L.fa_forward_ex.restype = ctypes.c_int
+        L.fa_backward.argtypes = [ctypes.POINTER(FaBwdParams), vp]
+        L.fa_backward.restype = ctypes.c_int
         L.fa_forward_packed_qkv.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]
         L.fa_forward_packed_qkv.restype = ctypes.c_int
         L.fa_forward_packed_qkv_ex.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, i32, i32, vp]

@@ -128,6 +128,45 @@ def attention(Q, K, V, causal=False, scale=None, return_lse=False, out_f32=False
     return (O, lse) if return_lse else O
 
 
+def backward_supported(Q) -> bool:
+    """Whether fa_backward has a kernel instance for Q's dtype and head dim (bf16 / fp16, head_dim % 8 == 0, <= 128)."""
+    return Q.dtype in (torch.bfloat16, torch.float16) and Q.shape[-1] % 8 == 0 and Q.shape[-1] <= 128
+
+
+def attention_backward(Q, K, V, O, LSE, dO, causal=False, scale=None):
+    """(dQ, dK, dV) of O = softmax(scale * Q K^T [+ causal mask]) V through the tcgen05 backward kernels (include/fa_b200.h:
+    fa_backward; csrc/fa_bwd_sm100.cuh).  Q, K, V as for `attention` (K, V may have fewer heads in the 4-D form: their gradients are
+    summed over the group); O and LSE are what `attention(..., return_lse=True)` returned, dO is shaped like O.  bf16 / fp16,
+    head_dim <= 128; anything else raises FaError — there is no fallback inside this call."""
+    b, h, nq, nk, d, hk = _shape4(Q, K, V)
+    if not backward_supported(Q):
+        raise FaError(f"attention_backward: no kernel instance for dtype {Q.dtype} head_dim {d} (bf16 / fp16, head_dim % 8 == 0, <= 128)")
+    if O.shape != Q.shape or dO.shape != Q.shape or O.dtype != Q.dtype or dO.dtype != Q.dtype or not (O.is_cuda and dO.is_cuda):
+        raise FaError("attention_backward: O and dO must match Q's shape, dtype and device")
+    if LSE.dtype != torch.float32 or LSE.numel() != b * h * nq or not LSE.is_cuda:
+        raise FaError("attention_backward: LSE must be the forward's fp32 [batch, heads, n_q]")
+    if scale is None:
+        scale = 1.0 / math.sqrt(d)
+    q, k, v, o, do = (_tma_view(t) for t in (Q, K, V, O, dO))
+    lse = LSE.contiguous()
+    dq = torch.empty(Q.shape, dtype=Q.dtype, device=Q.device)
+    dk = torch.empty(K.shape, dtype=K.dtype, device=K.device)
+    dv = torch.empty(V.shape, dtype=V.dtype, device=V.device)
+    p = _lib.FaBwdParams()
+    p.q, p.k, p.v, p.o, p.d_o, p.lse = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr()
+    p.dq, p.dk, p.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    p.batch, p.heads, p.kv_heads, p.n_q, p.n_k = b, h, hk, nq, nk
+    p.head_dim, p.dtype, p.causal, p.scale = d, _dtype_code(Q), int(bool(causal)), float(scale)
+    for name, t in (("q", q), ("k", k), ("v", v), ("o", o), ("do", do), ("dq", dq), ("dk", dk), ("dv", dv)):
+        sb, sh, sn = _strides_bhn(t)
+        setattr(p, f"{name}_stride_b", sb)
+        setattr(p, f"{name}_stride_h", sh)
+        setattr(p, f"{name}_stride_n", sn)
+    with torch.cuda.device(Q.device):
+        _lib.check(_lib.lib().fa_backward(ctypes.byref(p), _stream_ptr(Q.device)), "fa_backward")
+    return dq, dk, dv
+
+
 def forward(Q, K, V, causal=False):
     """Reference operator `forward(Q_d, K_d, V_d, causal) -> O` (src/main.cpp:3; src/flashattention.cu:603-617).
 

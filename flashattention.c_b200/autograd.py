@@ -1,9 +1,11 @@
 """Autograd support for the forward operator (NOT part of the reference, which is forward only, nor of the hot path this
 repository rebuilds: SURVEY.md 8(f) lists a backward pass under "generality the reference lacks").
 
-`attention_autograd(Q, K, V, causal, scale)` runs the tcgen05 forward kernel and keeps (Q, K, V, O, LSE); its backward recomputes
-the probabilities from the saved LSE — no N x N tensor is ever kept — in blocks of query rows with plain torch matmuls (library
-GEMMs on the tensor cores: this is host-side plumbing around the kernel, not a kernel of this repository):
+`attention_autograd(Q, K, V, causal, scale)` runs the tcgen05 forward kernel and keeps (Q, K, V, O, LSE).  For bf16 / fp16 tensors
+with head_dim <= 128 the backward is the tcgen05 backward (api.attention_backward -> fa_backward, csrc/fa_bwd_sm100.cuh: a
+statistics pass, a dK/dV launch and a dQ launch, atomics-free).  Other cases (fp32 tensors, head_dim 256) recompute the probabilities
+from the saved LSE — no N x N tensor is ever kept — in blocks of query rows with plain torch matmuls (library GEMMs: host-side
+plumbing around the forward kernel, not a kernel of this repository).  Both compute
 
     P  = exp(scale * Q K^T - LSE)            D  = rowsum(dO * O)
     dV = P^T dO                              dS = P * (dO V^T - D)
@@ -30,6 +32,11 @@ class _Attention(torch.autograd.Function):
     def backward(ctx, d_o):
         q, k, v, o, lse = ctx.saved_tensors
         causal, scale = ctx.causal, ctx.scale
+        if api.backward_supported(q):
+            dq, dk, dv = api.attention_backward(q, k, v, o, lse, d_o, causal=causal, scale=scale)
+            return dq, dk, dv, None, None, None
+        if k.shape[:-2] != q.shape[:-2]:
+            raise api.FaError("the recomputation backward (fp32 tensors, head_dim > 128) needs K and V with Q's head count")
         shape = q.shape
         d = shape[-1]
         q3, k3, v3, o3, do3 = (t.reshape(-1, t.shape[-2], d) for t in (q, k, v, o, d_o.contiguous()))
@@ -63,9 +70,12 @@ class _Attention(torch.autograd.Function):
 
 def attention_autograd(Q, K, V, causal=False, scale=None, precise=False):
     """`attention` with gradients: O = softmax(scale * Q K^T [+ causal mask]) V through the tcgen05 forward kernel, backward by
-    blockwise recomputation from the saved LSE (module docstring).  Q, K, V: CUDA tensors [B*H, N, d] or [B, H, N, d]."""
-    if K.shape[:-2] != Q.shape[:-2] or V.shape != K.shape:
-        raise api.FaError("attention_autograd needs K and V with Q's batch and head counts (expand grouped K/V heads first)")
+    the tcgen05 backward kernels (bf16 / fp16, head_dim <= 128) or blockwise recomputation from the saved LSE (module docstring).
+    Q, K, V: CUDA tensors [B*H, N, d] or [B, H, N, d]; K, V may have fewer heads in the 4-D form when the backward kernel applies."""
+    if V.shape != K.shape:
+        raise api.FaError("attention_autograd: K and V shapes differ")
+    if K.shape[:-2] != Q.shape[:-2] and not api.backward_supported(Q):
+        raise api.FaError("attention_autograd: grouped K/V heads need the backward kernel (bf16 / fp16, head_dim <= 128); expand K/V first")
     if scale is None:
         scale = 1.0 / math.sqrt(Q.shape[-1])
     return _Attention.apply(Q, K, V, bool(causal), float(scale), bool(precise))

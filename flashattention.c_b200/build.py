@@ -43,7 +43,7 @@ def _stale(target: Path, sources) -> bool:
 
 def build_lib(force=False) -> Path:
     out = PKG / "libfa_b200.so"
-    srcs = [CSRC / "fa_api.cu", CSRC / "fa_fwd_sm100.cuh", CSRC / "fa_simt.cuh", CSRC / "ptx.cuh", ROOT / "include" / "fa_b200.h"]
+    srcs = [CSRC / "fa_api.cu", CSRC / "fa_fwd_sm100.cuh", CSRC / "fa_bwd_sm100.cuh", CSRC / "fa_simt.cuh", CSRC / "ptx.cuh", ROOT / "include" / "fa_b200.h"]
     if force or _stale(out, srcs):
         _run([NVCC, *NVCC_FLAGS, "--shared", "-o", out, CSRC / "fa_api.cu"])
     return out

@@ -19,6 +19,7 @@
 
 #include "fa_fwd_sm100.cuh"
 #include "fa_simt.cuh"
+#include "fa_bwd_sm100.cuh"
 
 namespace {
 
@@ -188,14 +189,15 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 4-D map over [batch, heads, n, d] with element strides (d contiguous); box = [128 bytes of d] x [128 rows].
+// 4-D map over [batch, heads, n, d] with element strides (d contiguous); box = [128 bytes of d] x [box_rows rows] (128; the
+// streamed tiles of the backward kernel: 64).
 // Encoded maps are kept in a small per-thread cache keyed by everything that goes into them: a repeated call on the
 // same tensors (the common case in a serving / benchmark loop) skips the four driver encodes.
 struct MapKey {
-  const void* ptr; int elem_size; int dt; int swizzle; int d; int64_t batch, heads, n, sb, sh, sn;
+  const void* ptr; int elem_size; int dt; int swizzle; int d; int64_t batch, heads, n, sb, sh, sn; int box_rows;
   bool operator==(const MapKey& o) const {
     return ptr == o.ptr && elem_size == o.elem_size && dt == o.dt && swizzle == o.swizzle && d == o.d && batch == o.batch &&
-           heads == o.heads && n == o.n && sb == o.sb && sh == o.sh && sn == o.sn;
+           heads == o.heads && n == o.n && sb == o.sb && sh == o.sh && sn == o.sn && box_rows == o.box_rows;
   }
 };
 constexpr int kMapCacheSize = 32;
@@ -205,11 +207,12 @@ thread_local MapCache t_map_cache;
 // `elem` is the fa_dtype of the tensor's elements.  The box is always 128 bytes of d wide: a head dim that does not fill
 // its last box (or is smaller than one box) is zero-filled on load and clipped on store by TMA.
 int make_map(CUtensorMap* out, const void* ptr, int elem_size, int elem, int64_t batch, int64_t heads, int64_t n, int d,
-             int64_t sb, int64_t sh, int64_t sn, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, bool tf32_convert = false) {
+             int64_t sb, int64_t sh, int64_t sn, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B, bool tf32_convert = false,
+             int box_rows = 128) {
   CUtensorMapDataType dt = elem == FA_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                          : elem == FA_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   if (elem == FA_F32 && tf32_convert) dt = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;  // TMA converts fp32 -> tf32 while loading
-  const MapKey key{ptr, elem_size, (int)dt, (int)swizzle, d, batch, heads, n, sb, sh, sn};
+  const MapKey key{ptr, elem_size, (int)dt, (int)swizzle, d, batch, heads, n, sb, sh, sn, box_rows};
   MapCache& mc = t_map_cache;
   for (int i = 0; i < mc.used; ++i)
     if (mc.key[i] == key) {
@@ -232,7 +235,7 @@ int make_map(CUtensorMap* out, const void* ptr, int elem_size, int elem, int64_t
     if (dims[i + 1] != 1) return FA_ERR_UNSUPPORTED;
     strides[i] = 16;
   }
-  cuuint32_t box[4] = {(cuuint32_t)(128 / elem_size), 128, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)(128 / elem_size), (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(out, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -265,6 +268,102 @@ int launch_tc(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& m
   kern<<<(unsigned)grid, fa::kNumThreads, T::kSmemBytes, st>>>(mq, mk, mv, mo, fp);
   FA_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
+// ---- backward (fa_bwd_sm100.cuh): statistics pass + the dK/dV launch + the dQ launch ----
+template <int kHeadDim, bool kF16, bool kDKV>
+int launch_bwd(const CUtensorMap& r1, const CUtensorMap& r2, const CUtensorMap& t1, const CUtensorMap& t2, const fa::BwdParams& bp,
+               dim3 grid, cudaStream_t st) {
+  using T = fa::BwdTraits<kHeadDim>;
+  auto kern = fa::fa_bwd_sm100_kernel<kHeadDim, kF16, kDKV>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  FA_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return FA_ERR_NO_DEVICE;
+  if (!attr_set[dev]) {
+    FA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::kSmemBytes));
+    attr_set[dev] = true;
+  }
+  kern<<<grid, fa::kBwdThreads, T::kSmemBytes, st>>>(r1, r2, t1, t2, bp);
+  FA_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FA_OK;
+}
+
+template <bool kDKV>
+int launch_bwd_d(int di, bool f16, const CUtensorMap& r1, const CUtensorMap& r2, const CUtensorMap& t1, const CUtensorMap& t2,
+                 const fa::BwdParams& bp, dim3 grid, cudaStream_t st) {
+  if (di == 64) return f16 ? launch_bwd<64, true, kDKV>(r1, r2, t1, t2, bp, grid, st) : launch_bwd<64, false, kDKV>(r1, r2, t1, t2, bp, grid, st);
+  if (di == 128) return f16 ? launch_bwd<128, true, kDKV>(r1, r2, t1, t2, bp, grid, st) : launch_bwd<128, false, kDKV>(r1, r2, t1, t2, bp, grid, st);
+  return FA_ERR_UNSUPPORTED;
+}
+
+int run_bwd(const fa_bwd_params* p, cudaStream_t st) {
+  const int dt = p->dtype;
+  const bool f16 = dt == FA_F16;
+  const int di = p->head_dim <= 64 ? 64 : 128;
+  const int64_t kv_heads = p->kv_heads > 0 ? p->kv_heads : p->heads;
+  const int64_t n_q_pad = (p->n_q + 127) / 128 * 128;
+  const int64_t rows_pad = p->batch * p->heads * n_q_pad;
+  int rc = FA_OK;
+  void* ws = nullptr;
+  void* ws_async = nullptr;
+  if ((rc = split_workspace(st, (size_t)rows_pad * 2 * sizeof(float), &ws, &ws_async))) return rc;
+  struct WsFree {
+    void* p; cudaStream_t st;
+    ~WsFree() { if (p) cudaFreeAsync(p, st); }
+  } ws_free{ws_async, st};
+  float* l2 = static_cast<float*>(ws);
+  float* dsum = l2 + rows_pad;
+  {
+    const int64_t blocks = (rows_pad + 7) / 8;
+    if (blocks > 0x7fffffff) return FA_ERR_INVALID_ARG;
+    if (f16)
+      fa::fa_bwd_prep_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(
+          static_cast<const __half*>(p->o), p->o_stride_b, p->o_stride_h, p->o_stride_n, static_cast<const __half*>(p->d_o), p->do_stride_b,
+          p->do_stride_h, p->do_stride_n, p->lse, l2, dsum, (int)p->heads, (int)p->n_q, (int)n_q_pad, p->head_dim, rows_pad);
+    else
+      fa::fa_bwd_prep_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(p->o), p->o_stride_b, p->o_stride_h, p->o_stride_n, static_cast<const __nv_bfloat16*>(p->d_o),
+          p->do_stride_b, p->do_stride_h, p->do_stride_n, p->lse, l2, dsum, (int)p->heads, (int)p->n_q, (int)n_q_pad, p->head_dim, rows_pad);
+    FA_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  CUtensorMap q128, g128, k128, v128, q64, g64, k64, v64;
+  if ((rc = make_map(&k128, p->k, 2, dt, p->batch, kv_heads, p->n_k, p->head_dim, p->k_stride_b, p->k_stride_h, p->k_stride_n, sw, false, 128))) return rc;
+  if ((rc = make_map(&v128, p->v, 2, dt, p->batch, kv_heads, p->n_k, p->head_dim, p->v_stride_b, p->v_stride_h, p->v_stride_n, sw, false, 128))) return rc;
+  if ((rc = make_map(&q64, p->q, 2, dt, p->batch, p->heads, p->n_q, p->head_dim, p->q_stride_b, p->q_stride_h, p->q_stride_n, sw, false, 64))) return rc;
+  if ((rc = make_map(&g64, p->d_o, 2, dt, p->batch, p->heads, p->n_q, p->head_dim, p->do_stride_b, p->do_stride_h, p->do_stride_n, sw, false, 64))) return rc;
+  if ((rc = make_map(&q128, p->q, 2, dt, p->batch, p->heads, p->n_q, p->head_dim, p->q_stride_b, p->q_stride_h, p->q_stride_n, sw, false, 128))) return rc;
+  if ((rc = make_map(&g128, p->d_o, 2, dt, p->batch, p->heads, p->n_q, p->head_dim, p->do_stride_b, p->do_stride_h, p->do_stride_n, sw, false, 128))) return rc;
+  if ((rc = make_map(&k64, p->k, 2, dt, p->batch, kv_heads, p->n_k, p->head_dim, p->k_stride_b, p->k_stride_h, p->k_stride_n, sw, false, 64))) return rc;
+  if ((rc = make_map(&v64, p->v, 2, dt, p->batch, kv_heads, p->n_k, p->head_dim, p->v_stride_b, p->v_stride_h, p->v_stride_n, sw, false, 64))) return rc;
+  fa::BwdParams bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.scale = p->scale;
+  bp.scale_log2 = p->scale * 1.4426950408889634f;
+  bp.n_q = (int)p->n_q; bp.n_k = (int)p->n_k; bp.heads = (int)p->heads; bp.kv_heads = (int)kv_heads; bp.batch = (int)p->batch;
+  bp.kv_group = (int)(p->heads / kv_heads);
+  bp.head_dim = p->head_dim;
+  bp.causal = p->causal != 0;
+  bp.causal_offset = (int)(p->n_k - p->n_q);
+  bp.n_q_pad = (int)n_q_pad;
+  bp.l2 = l2; bp.dsum = dsum;
+  {   // dV, dK: one CTA per 128 keys of a K/V head
+    fa::BwdParams b = bp;
+    b.out0 = p->dv; b.o0_sb = p->dv_stride_b; b.o0_sh = p->dv_stride_h; b.o0_sn = p->dv_stride_n;
+    b.out1 = p->dk; b.o1_sb = p->dk_stride_b; b.o1_sh = p->dk_stride_h; b.o1_sn = p->dk_stride_n;
+    const dim3 grid((unsigned)((p->n_k + 127) / 128), (unsigned)kv_heads, (unsigned)p->batch);
+    if ((rc = launch_bwd_d<true>(di, f16, k128, v128, q64, g64, b, grid, st))) return rc;
+  }
+  {   // dQ: one CTA per 128 query rows of a head
+    fa::BwdParams b = bp;
+    b.out0 = p->dq; b.o0_sb = p->dq_stride_b; b.o0_sh = p->dq_stride_h; b.o0_sn = p->dq_stride_n;
+    const dim3 grid((unsigned)((p->n_q + 127) / 128), (unsigned)p->heads, (unsigned)p->batch);
+    if ((rc = launch_bwd_d<false>(di, f16, q128, g128, k64, v64, b, grid, st))) return rc;
+  }
   return FA_OK;
 }
 
@@ -594,6 +693,31 @@ int fa_forward_ex(const fa_params* p, void* stream) {
     return FA_ERR_INVALID_ARG;
   }
   if (rc == FA_OK) t_last_impl = impl;
+  return rc;
+}
+
+int fa_backward(const fa_bwd_params* p, void* stream) {
+  if (!p || !p->q || !p->k || !p->v || !p->o || !p->d_o || !p->lse || !p->dq || !p->dk || !p->dv) return FA_ERR_INVALID_ARG;
+  if (p->batch <= 0 || p->heads <= 0 || p->n_q <= 0 || p->n_k <= 0 || p->head_dim <= 0) return FA_ERR_INVALID_ARG;
+  if (p->n_q > 0x3fffffff || p->n_k > 0x3fffffff || p->batch > 65535 || p->heads > 65535) return FA_ERR_INVALID_ARG;
+  if (!(p->scale > 0.f) || !std::isfinite(p->scale)) return FA_ERR_INVALID_ARG;
+  if (p->kv_heads < 0 || (p->kv_heads > 0 && (p->kv_heads > p->heads || p->heads % p->kv_heads != 0))) return FA_ERR_INVALID_ARG;
+  if (p->dtype != FA_BF16 && p->dtype != FA_F16) return p->dtype == FA_F32 ? FA_ERR_UNSUPPORTED : FA_ERR_INVALID_ARG;
+  if (p->head_dim % 8 != 0 || p->head_dim > 128) return FA_ERR_UNSUPPORTED;
+  // the epilogue writes 16-byte vectors; O is read element-wise
+  const void* outs[3] = {p->dq, p->dk, p->dv};
+  const int64_t ostr[9] = {p->dq_stride_b, p->dq_stride_h, p->dq_stride_n, p->dk_stride_b, p->dk_stride_h, p->dk_stride_n,
+                           p->dv_stride_b, p->dv_stride_h, p->dv_stride_n};
+  for (int i = 0; i < 3; ++i)
+    if (reinterpret_cast<uintptr_t>(outs[i]) & 15) return FA_ERR_ALIGNMENT;
+  for (int i = 0; i < 9; ++i)
+    if (ostr[i] % 8) return FA_ERR_ALIGNMENT;
+  int major = 0;
+  int rc = probe_device(&major);
+  if (rc) return rc;
+  if (major != 10) return FA_ERR_NO_DEVICE;
+  rc = run_bwd(p, static_cast<cudaStream_t>(stream));
+  if (rc == FA_OK) t_last_impl = FA_IMPL_TCGEN05;
   return rc;
 }
 

@@ -1,0 +1,405 @@
+// fa_bwd_sm100.cuh — FlashAttention backward for sm_100a (16-bit operands, head dim <= 128): dQ, dK, dV of
+// O = softmax(scale Q K^T [+ causal]) V from (Q, K, V, O, LSE, dO).  The reference is forward only (README.md:33 lists what
+// it leaves open); SURVEY §8 (f4) names the backward pass as the widening step after the forward rows.
+//
+// Two launches of ONE kernel template, both atomics-free and deterministic:
+//   kDKV = true   a CTA owns 128 keys of one K/V head (resident tiles K_j, V_j) and streams 64-row tiles of (Q, dO) of every
+//                 query head of its group:   S^T = K Q^T,  dP^T = V dO^T   (tcgen05.mma, A and B from SMEM, D in TMEM)
+//                 P^T = exp2(S^T c - LSE2[q]),  dS^T = P^T (dP^T - D[q])   (one thread per key row, statistics per column)
+//                 dV += P^T dO,  dK += dS^T Q                              (A = P^T / dS^T read straight from TMEM)
+//   kDKV = false  a CTA owns 128 query rows of one head (resident Q_i, dO_i) and streams 64-key tiles of (K, V):
+//                 S = Q K^T,  dP = dO V^T,  dS = P (dP - D[q])  (statistics per row, in registers),  dQ += dS K
+// i.e. 4 + 3 = 7 contractions instead of the 5 of a single-pass backward: recomputing S and dP in the second launch is what
+// buys the absence of a dQ reduction across CTAs (no atomics, no dQ workspace, bit-reproducible results), and every
+// contraction has exactly the operand forms the forward kernel uses (K-major SMEM x K-major SMEM; TMEM x MN-major SMEM), on
+// the tiles as TMA delivers them (SWIZZLE_128B boxes of 128 bytes x rows): a streamed tile is read K-major by the first two
+// contractions and MN-major by the accumulating ones.
+//
+// D[q] = rowsum(dO * O) and LSE2[q] = LSE * log2(e) come from fa_bwd_prep_kernel in a workspace whose rows are padded to a
+// multiple of 128 per (batch, head) (+inf / 0 in the padding and for rows that saw no key: P = exp2(x - inf) = 0 there).
+//
+// Pipeline: warp 4 lane 0 = TMA producer (kStages ring of streamed tile pairs), warp 5 lane 0 = MMA issuer, warps 0-3 = one
+// thread per TMEM lane.  S/dP are double-buffered in TMEM (2 x (64 + 64) columns), so the tensor pipe runs S, dP of step
+// i+1 while the four warps turn S, dP of step i into P, dS; the accumulators take columns [256, 256 + 2 d).
+// The scale of dS (dS_raw = scale * P (dP - D)) is applied once, to the finished dQ / dK accumulators.
+#pragma once
+#include "fa_simt.cuh"   // ld_as_float
+#include "ptx.cuh"
+
+namespace fa {
+
+struct BwdParams {
+  float scale;        // multiplies q.k (as in the forward)
+  float scale_log2;   // scale * log2(e)
+  int n_q, n_k, heads, kv_heads, batch;
+  int kv_group;       // query heads per K/V head
+  int head_dim;       // true head dim (<= the instance's; columns beyond it are zero in SMEM and never stored)
+  int causal, causal_offset;   // key j visible to row i iff j <= i + causal_offset (n_k - n_q)
+  int n_q_pad;        // row pitch of the statistics workspace per (batch, head): n_q rounded up to 128
+  const float* l2;    // [batch, heads, n_q_pad]
+  const float* dsum;  // [batch, heads, n_q_pad]
+  void* out0;         // kDKV: dV [batch, kv_heads, n_k, d]   else: dQ [batch, heads, n_q, d]   (element strides below)
+  int64_t o0_sb, o0_sh, o0_sn;
+  void* out1;         // kDKV: dK
+  int64_t o1_sb, o1_sh, o1_sn;
+};
+
+constexpr int kBwdThreads = 192;   // 4 compute warps + producer warp + MMA warp
+constexpr int kBwdRes = 128;       // rows of a resident tile (keys of the dK/dV launch, query rows of the dQ launch)
+constexpr int kBwdStr = 64;        // rows of a streamed tile
+
+template <int kHeadDim>
+struct BwdTraits {
+  static_assert(kHeadDim == 64 || kHeadDim == 128, "backward instances: 128- and 256-byte rows of 16-bit elements");
+  static constexpr int kDChunks = kHeadDim * 2 / 128;            // 128-byte column chunks per row
+  static constexpr int kResChunkBytes = kBwdRes * 128;           // one TMA box of a resident tile
+  static constexpr int kStrChunkBytes = kBwdStr * 128;           // one TMA box of a streamed tile
+  static constexpr int kResTileBytes = kDChunks * kResChunkBytes;
+  static constexpr int kStrTileBytes = kDChunks * kStrChunkBytes;
+  static constexpr int kStageBytes = 2 * kStrTileBytes;          // the streamed pair
+  static constexpr int kStages = kDChunks == 1 ? 6 : 4;
+  static constexpr int kStatsBytes = 2 * kBwdStr * 4;            // LSE2[64] | D[64] of a streamed (Q, dO) tile
+  static constexpr int kNumBarriers = 1 + 2 * kStages + 2 + 2 + 1;
+  static constexpr int kSmemBytes = 2 * kResTileBytes + kStages * (kStageBytes + kStatsBytes) + kNumBarriers * 8 + 16 + 1024;
+  static constexpr int kTmemAcc = 256;                           // acc0 at 256, acc1 at 256 + kHeadDim
+  static_assert(kTmemAcc + 2 * kHeadDim <= 512, "TMEM budget");
+  static_assert(kSmemBytes <= 227 * 1024, "SMEM budget");
+};
+
+enum : uint32_t { TAG_B_RES = 21, TAG_B_FULL = 22, TAG_B_EMPTY = 23, TAG_B_S = 24, TAG_B_P = 25, TAG_B_ACC = 26 };
+
+// plain (non-tensor) bulk copy global -> shared, completing on an mbarrier; 16-byte aligned on both sides, bytes % 16 == 0
+FA_DEVINL void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int kHeadDim, bool kF16, bool kDKV>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_constant__ CUtensorMap tm_r2,
+                    const __grid_constant__ CUtensorMap tm_t1, const __grid_constant__ CUtensorMap tm_t2, const BwdParams p) {
+  using T = BwdTraits<kHeadDim>;
+  extern __shared__ uint8_t bwd_smem_raw[];
+  const uint32_t smem0 = (smem_u32(bwd_smem_raw) + 1023u) & ~1023u;
+  const uint32_t sR1 = smem0;                                      // kDKV: K_j    else: Q_i
+  const uint32_t sR2 = sR1 + T::kResTileBytes;                     // kDKV: V_j    else: dO_i
+  const uint32_t sStage = sR2 + T::kResTileBytes;                  // [kStages][t1 | t2]   kDKV: (Q, dO)   else: (K, V)
+  const uint32_t sStats = sStage + T::kStages * T::kStageBytes;    // [kStages][LSE2[64] | D[64]]  (kDKV)
+  const uint32_t bar_res = sStats + T::kStages * T::kStatsBytes;
+  const uint32_t bar_full = bar_res + 8;                           // [kStages]
+  const uint32_t bar_empty = bar_full + 8 * T::kStages;            // [kStages]
+  const uint32_t bar_s = bar_empty + 8 * T::kStages;               // [2]  S, dP of TMEM buffer b complete
+  const uint32_t bar_p = bar_s + 16;                               // [2]  P, dS of TMEM buffer b written
+  const uint32_t bar_acc = bar_p + 16;                             // accumulators final
+  const uint32_t s_tmem_ptr = bar_acc + 8;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int batch = blockIdx.z;
+  const int head_r = blockIdx.y;                                   // head of the resident tiles (kDKV: a K/V head)
+  // the dQ launch takes its causal tiles heaviest (= last rows) first
+  const int tile = (!kDKV && p.causal) ? static_cast<int>(gridDim.x - 1 - blockIdx.x) : static_cast<int>(blockIdx.x);
+  const int row0 = tile * kBwdRes;
+
+  // ---- the streamed steps of this CTA ----
+  // kDKV: step -> (g, i): query head head_r * kv_group + g, rows [64 i, 64 i + 64), i from the first tile with a row that sees
+  //       one of this CTA's keys.  else: step j -> keys [64 j, 64 j + 64), up to the last key any of the CTA's rows sees.
+  int i_first = 0, per_head = 0, n_steps = 0;
+  if (kDKV) {
+    const int nq64 = (p.n_q + kBwdStr - 1) / kBwdStr;
+    if (p.causal) i_first = max(0, row0 - p.causal_offset) / kBwdStr;
+    per_head = max(0, nq64 - i_first);
+    n_steps = per_head * p.kv_group;
+  } else {
+    int last = p.n_k - 1;
+    if (p.causal) last = min(last, min(row0 + kBwdRes - 1, p.n_q - 1) + p.causal_offset);
+    n_steps = last < 0 ? 0 : last / kBwdStr + 1;
+  }
+
+  if (warp == 5 && lane == 0) {
+    mbar_init(bar_res, 1);
+    for (int i = 0; i < T::kStages; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_s + 8 * b, 1);
+      mbar_init(bar_p + 8 * b, 128);
+    }
+    mbar_init(bar_acc, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_r1);
+      tma_prefetch_desc(&tm_r2);
+      tma_prefetch_desc(&tm_t1);
+      tma_prefetch_desc(&tm_t2);
+    }
+    tmem_alloc(s_tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem_ptr));
+
+  if (warp == 4) {
+    // =========================== TMA producer ===========================
+    if (lane == 0 && n_steps > 0) {
+      mbar_arrive_expect_tx(bar_res, 2 * T::kResTileBytes);
+#pragma unroll
+      for (int c = 0; c < T::kDChunks; ++c) {
+        tma_load_4d(sR1 + c * T::kResChunkBytes, &tm_r1, bar_res, c * 64, row0, head_r, batch);
+        tma_load_4d(sR2 + c * T::kResChunkBytes, &tm_r2, bar_res, c * 64, row0, head_r, batch);
+      }
+      for (int step = 0; step < n_steps; ++step) {
+        const int st = step % T::kStages;
+        if (step >= T::kStages) mbar_wait(bar_empty + 8 * st, ((step / T::kStages) - 1) & 1, TAG_B_EMPTY);
+        int head_t, srow;
+        if (kDKV) {
+          head_t = head_r * p.kv_group + step / per_head;
+          srow = (i_first + step % per_head) * kBwdStr;
+        } else {
+          head_t = head_r / p.kv_group;
+          srow = step * kBwdStr;
+        }
+        const uint32_t dst = sStage + st * T::kStageBytes;
+        mbar_arrive_expect_tx(bar_full + 8 * st, T::kStageBytes + (kDKV ? T::kStatsBytes : 0));
+#pragma unroll
+        for (int c = 0; c < T::kDChunks; ++c) {
+          tma_load_4d(dst + c * T::kStrChunkBytes, &tm_t1, bar_full + 8 * st, c * 64, srow, head_t, batch);
+          tma_load_4d(dst + T::kStrTileBytes + c * T::kStrChunkBytes, &tm_t2, bar_full + 8 * st, c * 64, srow, head_t, batch);
+        }
+        if (kDKV) {
+          const int64_t off = (static_cast<int64_t>(batch) * p.heads + head_t) * p.n_q_pad + srow;
+          bulk_load(sStats + st * T::kStatsBytes, p.l2 + off, kBwdStr * 4, bar_full + 8 * st);
+          bulk_load(sStats + st * T::kStatsBytes + kBwdStr * 4, p.dsum + off, kBwdStr * 4, bar_full + 8 * st);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0 && n_steps > 0) {
+      constexpr uint32_t kFmt = kF16 ? 0u : 1u;
+      constexpr uint32_t idesc_sd = make_idesc(kFmt, 0, kBwdRes, kBwdStr);      // S, dP: 128 x 64, both operands K-major
+      constexpr uint32_t idesc_acc = make_idesc(kFmt, 1, kBwdRes, kHeadDim);    // accumulators: 128 x d, B MN-major
+      constexpr uint64_t hi_kmajor = make_sdesc_hi_sw128(16, 1024);
+      // a streamed tile as the MN-major B operand (N = d, K = its 64 rows): LBO = stride between the 128-byte column chunks,
+      // SBO = stride between 8-row groups
+      constexpr uint64_t hi_mnmajor = make_sdesc_hi_sw128(T::kStrChunkBytes, 1024);
+      constexpr int kKStepsD = kHeadDim / 16;       // k-steps over the head dim (S, dP)
+      constexpr int kKStepsR = kBwdStr / 16;        // k-steps over the streamed rows (accumulators)
+      mbar_wait(bar_res, 0, TAG_B_RES);
+      tc_fence_after();
+      const uint64_t r1d = sdesc_at(hi_kmajor, sR1);
+      const uint64_t r2d = sdesc_at(hi_kmajor, sR2);
+      auto issue_sd = [&](int step) {
+        const int st = step % T::kStages;
+        const uint32_t b = static_cast<uint32_t>(step & 1);
+        mbar_wait(bar_full + 8 * st, (step / T::kStages) & 1, TAG_B_FULL);
+        tc_fence_after();
+        const uint64_t t1d = sdesc_at(hi_kmajor, sStage + st * T::kStageBytes);
+        const uint64_t t2d = sdesc_at(hi_kmajor, sStage + st * T::kStageBytes + T::kStrTileBytes);
+        const uint32_t dS = tmem_base + b * 128u;
+#pragma unroll
+        for (int kk = 0; kk < kKStepsD; ++kk) {
+          const uint32_t offr = ((kk >> 2) * T::kResChunkBytes + (kk & 3) * 32) >> 4;
+          const uint32_t offt = ((kk >> 2) * T::kStrChunkBytes + (kk & 3) * 32) >> 4;
+          mma_ss<false>(dS, r1d + offr, t1d + offt, idesc_sd, kk > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int kk = 0; kk < kKStepsD; ++kk) {
+          const uint32_t offr = ((kk >> 2) * T::kResChunkBytes + (kk & 3) * 32) >> 4;
+          const uint32_t offt = ((kk >> 2) * T::kStrChunkBytes + (kk & 3) * 32) >> 4;
+          mma_ss<false>(dS + 64u, r2d + offr, t2d + offt, idesc_sd, kk > 0 ? 1u : 0u);
+        }
+        tc_commit(bar_s + 8 * b);
+      };
+      issue_sd(0);
+      for (int step = 0; step < n_steps; ++step) {
+        if (step + 1 < n_steps) issue_sd(step + 1);
+        const int st = step % T::kStages;
+        const uint32_t b = static_cast<uint32_t>(step & 1);
+        mbar_wait(bar_p + 8 * b, (step >> 1) & 1, TAG_B_P);
+        tc_fence_after();
+        const uint64_t t1m = sdesc_at(hi_mnmajor, sStage + st * T::kStageBytes);
+        const uint64_t t2m = sdesc_at(hi_mnmajor, sStage + st * T::kStageBytes + T::kStrTileBytes);
+        const uint32_t aP = tmem_base + b * 128u;          // P (packed pairs) over the first 32 columns of S
+        const uint32_t aDS = tmem_base + b * 128u + 64u;   // dS over the first 32 columns of dP
+        const uint32_t acc0 = tmem_base + T::kTmemAcc;
+        const uint32_t acc1 = acc0 + kHeadDim;
+        if (kDKV) {
+#pragma unroll
+          for (int ks = 0; ks < kKStepsR; ++ks)   // dV += P^T dO
+            mma_ts<false>(acc0, aP + ks * 8, t2m + static_cast<uint32_t>(ks * 128), idesc_acc, (step > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < kKStepsR; ++ks)   // dK += dS^T Q
+            mma_ts<false>(acc1, aDS + ks * 8, t1m + static_cast<uint32_t>(ks * 128), idesc_acc, (step > 0 || ks > 0) ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < kKStepsR; ++ks)   // dQ += dS K
+            mma_ts<false>(acc0, aDS + ks * 8, t1m + static_cast<uint32_t>(ks * 128), idesc_acc, (step > 0 || ks > 0) ? 1u : 0u);
+        }
+        tc_commit(bar_empty + 8 * st);   // the stage's tiles (and this buffer's P, dS) have been read once these complete
+      }
+      tc_commit(bar_acc);
+    }
+  } else {
+    // =========================== P, dS (one thread per TMEM lane) + epilogue ===========================
+    const int r = warp * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const int my_row = row0 + r;          // kDKV: key index    else: query row
+    float l2r = INFINITY, dr = 0.f;       // dQ launch: the row's statistics
+    if (!kDKV) {
+      const int64_t off = (static_cast<int64_t>(batch) * p.heads + head_r) * p.n_q_pad + my_row;   // my_row < n_q_pad always
+      l2r = p.l2[off];
+      dr = p.dsum[off];
+    }
+    const bool row_valid = kDKV ? (my_row < p.n_k) : true;   // (query rows beyond n_q have LSE2 = +inf)
+    for (int step = 0; step < n_steps; ++step) {
+      const int st = step % T::kStages;
+      const uint32_t b = static_cast<uint32_t>(step & 1);
+      if (kDKV) mbar_wait(bar_full + 8 * st, (step / T::kStages) & 1, TAG_B_FULL);   // the statistics of this stage
+      mbar_wait(bar_s + 8 * b, (step >> 1) & 1, TAG_B_S);
+      tc_fence_after();
+      const uint32_t tS = tmem_base + lane_base + b * 128u;
+      const uint32_t tDP = tS + 64u;
+      float s[64], dp[64];
+      tmem_ld32(tS, reinterpret_cast<uint32_t*>(&s[0]));
+      tmem_ld32(tS + 32, reinterpret_cast<uint32_t*>(&s[32]));
+      tmem_ld32(tDP, reinterpret_cast<uint32_t*>(&dp[0]));
+      tmem_ld32(tDP + 32, reinterpret_cast<uint32_t*>(&dp[32]));
+      tc_wait_ld();
+      // column c of this step is visible to this thread's row iff c_lo <= c <= c_hi
+      int c_lo = 0, c_hi = kBwdStr - 1;
+      if (kDKV) {
+        const int q0 = (i_first + step % per_head) * kBwdStr;
+        if (p.causal) c_lo = my_row - p.causal_offset - q0;            // q0 + c + offset >= key
+        if (!row_valid) c_lo = kBwdStr;
+      } else {
+        const int k0 = step * kBwdStr;
+        c_hi = p.n_k - 1 - k0;
+        if (p.causal) c_hi = min(c_hi, my_row + p.causal_offset - k0);
+      }
+      const bool masked = c_lo > 0 || c_hi < kBwdStr - 1;
+      uint32_t ppk[32], dpk[32];
+      const uint32_t s_l2 = sStats + st * T::kStatsBytes;
+      const uint32_t s_d = s_l2 + kBwdStr * 4;
+#pragma unroll
+      for (int c4 = 0; c4 < kBwdStr / 4; ++c4) {
+        float lq[4], dq[4];
+        if (kDKV) {
+          uint32_t a0, a1, a2, a3, d0, d1, d2, d3;
+          ld_shared_v4(s_l2 + c4 * 16, a0, a1, a2, a3);
+          ld_shared_v4(s_d + c4 * 16, d0, d1, d2, d3);
+          lq[0] = __uint_as_float(a0); lq[1] = __uint_as_float(a1); lq[2] = __uint_as_float(a2); lq[3] = __uint_as_float(a3);
+          dq[0] = __uint_as_float(d0); dq[1] = __uint_as_float(d1); dq[2] = __uint_as_float(d2); dq[3] = __uint_as_float(d3);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { lq[u] = l2r; dq[u] = dr; }
+        }
+        float pv[4], dv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c4 * 4 + u;
+          float e = ex2(fmaf(s[c], p.scale_log2, -lq[u]));
+          if (masked && (c < c_lo || c > c_hi)) e = 0.f;
+          pv[u] = e;
+          dv[u] = e * (dp[c] - dq[u]);
+        }
+        ppk[c4 * 2] = pack_16x2<kF16>(pv[0], pv[1]);
+        ppk[c4 * 2 + 1] = pack_16x2<kF16>(pv[2], pv[3]);
+        dpk[c4 * 2] = pack_16x2<kF16>(dv[0], dv[1]);
+        dpk[c4 * 2 + 1] = pack_16x2<kF16>(dv[2], dv[3]);
+      }
+      if (kDKV) tmem_st32(tS, ppk);     // P^T over S (every S column is in registers by now)
+      tmem_st32(tDP, dpk);              // dS over dP
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_p + 8 * b);
+    }
+
+    // ---- epilogue: accumulators -> (scale) -> 16-bit -> global, one row per thread ----
+    const bool have = n_steps > 0;
+    if (have) {
+      mbar_wait(bar_acc, 0, TAG_B_ACC);
+      tc_fence_after();
+    }
+    const int n_rows = kDKV ? p.n_k : p.n_q;
+    auto store_acc = [&](uint32_t tcol, float mul, void* out, int64_t sb, int64_t sh, int64_t sn) {
+      uint8_t* dst = static_cast<uint8_t*>(out) + 2 * (batch * sb + head_r * sh + static_cast<int64_t>(my_row) * sn);
+#pragma unroll
+      for (int cc = 0; cc < kHeadDim / 32; ++cc) {
+        uint32_t v[32];
+        if (have) {
+          tmem_ld32(tmem_base + lane_base + tcol + cc * 32, v);
+          tc_wait_ld();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        if (my_row < n_rows) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int col = cc * 32 + q4 * 8;
+            if (col < p.head_dim) {
+              uint4 pk;
+              pk.x = pack_16x2<kF16>(__uint_as_float(v[q4 * 8 + 0]) * mul, __uint_as_float(v[q4 * 8 + 1]) * mul);
+              pk.y = pack_16x2<kF16>(__uint_as_float(v[q4 * 8 + 2]) * mul, __uint_as_float(v[q4 * 8 + 3]) * mul);
+              pk.z = pack_16x2<kF16>(__uint_as_float(v[q4 * 8 + 4]) * mul, __uint_as_float(v[q4 * 8 + 5]) * mul);
+              pk.w = pack_16x2<kF16>(__uint_as_float(v[q4 * 8 + 6]) * mul, __uint_as_float(v[q4 * 8 + 7]) * mul);
+              *reinterpret_cast<uint4*>(dst + col * 2) = pk;
+            }
+          }
+        }
+      }
+    };
+    if (kDKV) {
+      store_acc(T::kTmemAcc, 1.0f, p.out0, p.o0_sb, p.o0_sh, p.o0_sn);                    // dV
+      store_acc(T::kTmemAcc + kHeadDim, p.scale, p.out1, p.o1_sb, p.o1_sh, p.o1_sn);      // dK
+    } else {
+      store_acc(T::kTmemAcc, p.scale, p.out0, p.o0_sb, p.o0_sh, p.o0_sn);                 // dQ
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// D[row] = sum_c dO[row, c] * O[row, c] and LSE2[row] = LSE[row] * log2(e) into the padded workspace; one warp per padded row.
+template <typename T16>
+__global__ void __launch_bounds__(256)
+fa_bwd_prep_kernel(const T16* __restrict__ o, int64_t o_sb, int64_t o_sh, int64_t o_sn, const T16* __restrict__ d_o, int64_t g_sb,
+                   int64_t g_sh, int64_t g_sn, const float* __restrict__ lse, float* __restrict__ l2, float* __restrict__ dsum,
+                   int heads, int n_q, int n_q_pad, int d, int64_t rows_pad) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (idx >= rows_pad) return;
+  const int64_t bh = idx / n_q_pad;
+  const int row = static_cast<int>(idx % n_q_pad);
+  float acc = 0.f, l = INFINITY;
+  if (row < n_q) {
+    const int64_t b = bh / heads, h = bh % heads;
+    const T16* po = o + b * o_sb + h * o_sh + static_cast<int64_t>(row) * o_sn;
+    const T16* pg = d_o + b * g_sb + h * g_sh + static_cast<int64_t>(row) * g_sn;
+    for (int c = lane; c < d; c += 32) acc = fmaf(ld_as_float(po + c), ld_as_float(pg + c), acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    const float x = lse[bh * n_q + row];
+    l = (x == -INFINITY) ? INFINITY : x * 1.4426950408889634f;
+  }
+  if (lane == 0) {
+    l2[idx] = l;
+    dsum[idx] = acc;
+  }
+}
+
+}  // namespace fa

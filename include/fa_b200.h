@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define FA_B200_VERSION 101 /* major*100 + minor */
+#define FA_B200_VERSION 102 /* major*100 + minor */
 
 /* element type of Q, K, V (and of O unless stated otherwise) */
 enum fa_dtype {
@@ -122,6 +122,34 @@ int fa_forward_packed_qkv(const float* inp, float* out, float* lse,
 int fa_forward_packed_qkv_ex(const float* inp, float* out, float* lse,
                              int32_t B, int32_t T, int32_t NH, int32_t hs,
                              float scale, int32_t causal, int32_t flags, void* stream);
+
+/*
+ * fa_backward — gradients of O = softmax(scale Q K^T [+ causal]) V: dQ, dK, dV from (Q, K, V, O, LSE, dO).  The reference is
+ * forward only (README.md:33 lists what it leaves open); this is the step after its operator for a training caller, on the same
+ * tcgen05 / TMEM / TMA machinery: a statistics pass (D = rowsum(dO * O)), one launch that owns 128 keys per CTA and accumulates
+ * dK, dV over the query tiles, and one that owns 128 query rows per CTA and accumulates dQ over the key tiles — no atomics, so
+ * results are bit-reproducible.  bf16 and fp16, head_dim <= 128 (% 8 == 0); FA_F32 returns FA_ERR_UNSUPPORTED.  LSE is the
+ * forward's ([batch, heads, n_q] contiguous fp32); O and dO are [batch, heads, n_q, head_dim]; dQ is shaped like Q, dK and dV
+ * like K and V ([batch, kv_heads, n_k, head_dim]: with grouped K/V heads they are summed over the group's query heads).  Strides
+ * are in ELEMENTS with the head_dim axis contiguous; gradient pointers and strides must be 16-byte aligned.
+ */
+typedef struct fa_bwd_params {
+  const void* q; const void* k; const void* v; const void* o; const void* d_o;
+  const float* lse;
+  void* dq; void* dk; void* dv;
+  int64_t batch, heads, kv_heads /* 0 = heads */, n_q, n_k;
+  int32_t head_dim, dtype, causal;
+  float scale;
+  int64_t q_stride_b, q_stride_h, q_stride_n;
+  int64_t k_stride_b, k_stride_h, k_stride_n;
+  int64_t v_stride_b, v_stride_h, v_stride_n;
+  int64_t o_stride_b, o_stride_h, o_stride_n;
+  int64_t do_stride_b, do_stride_h, do_stride_n;
+  int64_t dq_stride_b, dq_stride_h, dq_stride_n;
+  int64_t dk_stride_b, dk_stride_h, dk_stride_n;
+  int64_t dv_stride_b, dv_stride_h, dv_stride_n;
+} fa_bwd_params;
+int fa_backward(const fa_bwd_params* p, void* stream);
 
 /*
  * fa_forward_host — the same operator with HOST buffers: copies Q, K, V to the device, runs

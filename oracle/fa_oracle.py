@@ -8,6 +8,8 @@ TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.
   f64(q, k, v, scale, causal)        float64 softmax(scale*QK^T [+mask]) V (bench_flashattention.py:36-48 + scale)
   llmc_cpu(inp, B, T, C, NH)         the llm.c CPU loop (src/llm.c/attention_forward.cu:53-125)
   numpy_f64(q, k, v, scale, causal)  same maths as f64() written with numpy only (cross-check of the C code)
+  backward_f64(q, k, v, d_o, ...)    float64 gradients (dQ, dK, dV) of that operator, written out analytically (the reference has no
+                                      backward — README.md:33 — so this is pinned by central differences of numpy_f64, not by it)
   ref_llmc_cpu(inp, B, T, C, NH)     the REFERENCE's attention_forward_cpu itself, from oracle/_ref/libllmc_ref.so
                                       (only where /root/reference was compiled; returns None otherwise)
 """
@@ -103,8 +105,10 @@ def merge(o_acc, lse_acc, o_new, lse_new):
 
 def numpy_f64(q, k, v, scale=1.0, causal=False):
     """Independent numpy evaluation (small sizes): -> (O float64, LSE float64)."""
-    q3, k3, v3, shape = _flatten(q, k, v)
-    q3, k3, v3 = q3.astype(np.float64), k3.astype(np.float64), v3.astype(np.float64)
+    q, k, v = (np.asarray(t, dtype=np.float64) for t in (q, k, v))   # (float64 inputs are used as they are)
+    shape, d = q.shape, q.shape[-1]
+    q3, k3, v3 = q.reshape(-1, q.shape[-2], d), k.reshape(-1, k.shape[-2], d), v.reshape(-1, v.shape[-2], d)
+    assert k3.shape == v3.shape and k3.shape[0] == q3.shape[0]
     s = np.einsum("bid,bjd->bij", q3, k3) * scale
     if causal:
         n_q, n_k = q3.shape[1], k3.shape[1]
@@ -119,6 +123,37 @@ def numpy_f64(q, k, v, scale=1.0, causal=False):
         o = np.where(l > 0, np.einsum("bij,bjd->bid", p, v3) / l, 0.0)
         lse = np.where(l[..., 0] > 0, mx[..., 0] + np.log(l[..., 0]), -np.inf)
     return o.reshape(shape), lse.reshape(shape[:-1])
+
+
+def backward_f64(q, k, v, d_o, scale=1.0, causal=False):
+    """float64 (dQ, dK, dV) of O = softmax(scale Q K^T [+ causal mask]) V contracted with d_o.  q, d_o: [B, H, n_q, d]; k, v:
+    [B, H_kv, n_k, d] with H % H_kv == 0 (query head h reads K/V head h // (H / H_kv); their gradients sum over the group).
+        P = softmax(S),  D = rowsum(dO * O),  dV = P^T dO,  dS = P (dO V^T - D),  dQ = scale dS K,  dK = scale dS^T Q"""
+    q, k, v, d_o = (np.asarray(t, dtype=np.float64) for t in (q, k, v, d_o))
+    B, H, n_q, d = q.shape
+    Hk, n_k = k.shape[1], k.shape[2]
+    g = H // Hk
+    kk = np.repeat(k, g, axis=1)
+    vv = np.repeat(v, g, axis=1)
+    s = np.einsum("bhid,bhjd->bhij", q, kk) * scale
+    if causal:
+        i = np.arange(n_q)[:, None]
+        j = np.arange(n_k)[None, :]
+        s = np.where(j <= i + (n_k - n_q), s, -np.inf)
+    mx = s.max(axis=-1, keepdims=True)
+    mx = np.where(np.isfinite(mx), mx, 0.0)
+    p = np.exp(s - mx)
+    l = p.sum(axis=-1, keepdims=True)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        p = np.where(l > 0, p / l, 0.0)
+    o = np.einsum("bhij,bhjd->bhid", p, vv)
+    delta = (d_o * o).sum(-1, keepdims=True)
+    dp = np.einsum("bhid,bhjd->bhij", d_o, vv)
+    ds = p * (dp - delta)
+    dq = scale * np.einsum("bhij,bhjd->bhid", ds, kk)
+    dk = scale * np.einsum("bhij,bhid->bhjd", ds, q).reshape(B, Hk, g, n_k, d).sum(2)
+    dv = np.einsum("bhij,bhid->bhjd", p, d_o).reshape(B, Hk, g, n_k, d).sum(2)
+    return dq, dk, dv
 
 
 def packed_qkv_to_bhnd(inp, B, T, C, NH):

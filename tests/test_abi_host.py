@@ -82,7 +82,7 @@ def test_tma_view_passes_aligned_strided_views_and_copies_the_rest():
 
 def test_version_and_strerror(fab):
     L = fab.lib()
-    assert L.fa_version() == 101
+    assert L.fa_version() == 102
     assert L.fa_strerror(0) == b"ok"
     assert b"no CPU fallback" in L.fa_strerror(-2)
     assert L.fa_strerror(-12345) == b"unknown status"
@@ -102,6 +102,59 @@ def test_kernel_dispatch_table(fab):
         assert [q(dt, d) for d in (8, 64, 72, 128, 136, 256)] == [64, 64, 128, 128, 256, 256]
         assert q(dt, 12) == -4 and q(dt, 264) == -4
     assert q(7, 64) == -1 and q(F32, 0) == -1
+
+
+def test_backward_struct_layout_matches_the_header(tmp_path):
+    """fa_bwd_params: gcc's layout of the header == the ctypes mirror."""
+    sys.path.insert(0, str(ROOT))
+    from flashattention_c_b200 import _lib
+
+    fields = [f[0] for f in _lib.FaBwdParams._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "fa_b200.h"}"', 'int main(void) {',
+            '  printf("%zu\\n", sizeof(fa_bwd_params));']
+    prog += [f'  printf("%zu\\n", offsetof(fa_bwd_params, {f}));' for f in fields]
+    prog += ['  return 0; }']
+    src = tmp_path / "layout_bwd.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout_bwd"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == ctypes.sizeof(_lib.FaBwdParams)
+    for f, off in zip(fields, out[1:]):
+        assert int(off) == getattr(_lib.FaBwdParams, f).offset, f
+
+
+def test_backward_arguments_are_rejected_before_touching_a_device(fab):
+    from flashattention_c_b200 import _lib
+    L = fab.lib()
+    buf = (ctypes.c_float * 64)()
+    ptr = ctypes.cast(buf, ctypes.c_void_p).value
+    ptr = (ptr + 15) & ~15
+
+    def params(**kw):
+        p = _lib.FaBwdParams()
+        for n in ("q", "k", "v", "o", "d_o", "lse", "dq", "dk", "dv"):
+            setattr(p, n, ptr)
+        p.batch, p.heads, p.kv_heads, p.n_q, p.n_k, p.head_dim, p.dtype, p.causal, p.scale = 1, 2, 0, 16, 16, 64, _lib.FA_BF16, 0, 1.0
+        for t in ("q", "k", "v", "o", "do", "dq", "dk", "dv"):
+            setattr(p, f"{t}_stride_b", 2 * 16 * 64)
+            setattr(p, f"{t}_stride_h", 16 * 64)
+            setattr(p, f"{t}_stride_n", 64)
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    assert L.fa_backward(None, None) == -1
+    assert L.fa_backward(ctypes.byref(params(dq=None)), None) == -1          # null gradient pointer
+    assert L.fa_backward(ctypes.byref(params(n_k=0)), None) == -1
+    assert L.fa_backward(ctypes.byref(params(scale=0.0)), None) == -1
+    assert L.fa_backward(ctypes.byref(params(kv_heads=3)), None) == -1       # heads % kv_heads
+    assert L.fa_backward(ctypes.byref(params(dtype=_lib.FA_F32)), None) == -4   # fp32: no backward instance (unsupported, not invalid)
+    assert L.fa_backward(ctypes.byref(params(head_dim=256)), None) == -4
+    assert L.fa_backward(ctypes.byref(params(dq=ptr + 4)), None) == -5       # misaligned gradient pointer
+    assert L.fa_backward(ctypes.byref(params(dk_stride_n=68)), None) == -5   # gradient stride not a multiple of 16 bytes
+    if not torch.cuda.is_available():
+        assert L.fa_backward(ctypes.byref(params()), None) == -2            # FA_ERR_NO_DEVICE: no fallback
 
 
 def test_invalid_arguments_are_rejected_before_touching_a_device(fab):
