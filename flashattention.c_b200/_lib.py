@@ -3,10 +3,12 @@ returns an error there is NO fallback path — an exception is raised."""
 from __future__ import annotations
 
 import ctypes
+import os
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libfa_b200.so"
+# FA_B200_LIB: another build of the same library (A/B and tracing variants under flashattention.c_b200/variants/)
+LIB_PATH = Path(os.environ.get("FA_B200_LIB") or PKG_DIR / "libfa_b200.so")
 
 FA_F32, FA_BF16, FA_F16 = 0, 1, 2
 FA_IMPL_AUTO, FA_IMPL_TCGEN05, FA_IMPL_SIMT = 0, 1, 2

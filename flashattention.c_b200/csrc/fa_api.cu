@@ -351,16 +351,47 @@ int run_bwd(const fa_bwd_params* p, cudaStream_t st) {
   bp.causal_offset = (int)(p->n_k - p->n_q);
   bp.n_q_pad = (int)n_q_pad;
   bp.l2 = l2; bp.dsum = dsum;
+  bp.trace = nullptr;
+#if FA_BWD_TRACE
+  // tracing build: FA_B200_BWD_TRACE=path dumps the timeline of CTA (0,0,0) of the dK/dV launch (FA_B200_BWD_TRACE_DQ=1: of the dQ launch)
+  static unsigned long long* d_btrace = nullptr;
+  const char* btrace_path = getenv("FA_B200_BWD_TRACE");
+  const bool btrace_dq = getenv("FA_B200_BWD_TRACE_DQ") != nullptr;
+  const size_t btrace_n = 4 * 32 * 8;
+  if (btrace_path) {
+    if (!d_btrace) FA_CUDA(cudaMalloc(&d_btrace, btrace_n * sizeof(unsigned long long)));
+    FA_CUDA(cudaMemsetAsync(d_btrace, 0, btrace_n * sizeof(unsigned long long), st));
+  }
+  struct BTraceDump {
+    const char* path; unsigned long long* dev; size_t n; cudaStream_t st;
+    ~BTraceDump() {
+      if (!path) return;
+      cudaStreamSynchronize(st);
+      std::vector<unsigned long long> h(n);
+      cudaMemcpy(h.data(), dev, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+      if (FILE* f = fopen(path, "w")) {
+        for (size_t i = 0; i < n; ++i) fprintf(f, "%llu%c", h[i], (i % 8 == 7) ? '\n' : ' ');
+        fclose(f);
+      }
+    }
+  } btrace_dump{btrace_path, d_btrace, btrace_n, st};
+#endif
   {   // dV, dK: one CTA per 128 keys of a K/V head
     fa::BwdParams b = bp;
     b.out0 = p->dv; b.o0_sb = p->dv_stride_b; b.o0_sh = p->dv_stride_h; b.o0_sn = p->dv_stride_n;
     b.out1 = p->dk; b.o1_sb = p->dk_stride_b; b.o1_sh = p->dk_stride_h; b.o1_sn = p->dk_stride_n;
+#if FA_BWD_TRACE
+    if (btrace_path && !btrace_dq) b.trace = d_btrace;
+#endif
     const dim3 grid((unsigned)((p->n_k + 127) / 128), (unsigned)kv_heads, (unsigned)p->batch);
     if ((rc = launch_bwd_d<true>(di, f16, k128, v128, q64, g64, b, grid, st))) return rc;
   }
   {   // dQ: one CTA per 128 query rows of a head
     fa::BwdParams b = bp;
     b.out0 = p->dq; b.o0_sb = p->dq_stride_b; b.o0_sh = p->dq_stride_h; b.o0_sn = p->dq_stride_n;
+#if FA_BWD_TRACE
+    if (btrace_path && btrace_dq) b.trace = d_btrace;
+#endif
     const dim3 grid((unsigned)((p->n_q + 127) / 128), (unsigned)p->heads, (unsigned)p->batch);
     if ((rc = launch_bwd_d<false>(di, f16, q128, g128, k64, v64, b, grid, st))) return rc;
   }

@@ -18,13 +18,30 @@
 // D[q] = rowsum(dO * O) and LSE2[q] = LSE * log2(e) come from fa_bwd_prep_kernel in a workspace whose rows are padded to a
 // multiple of 128 per (batch, head) (+inf / 0 in the padding and for rows that saw no key: P = exp2(x - inf) = 0 there).
 //
-// Pipeline: warp 4 lane 0 = TMA producer (kStages ring of streamed tile pairs), warp 5 lane 0 = MMA issuer, warps 0-3 = one
-// thread per TMEM lane.  S/dP are double-buffered in TMEM (2 x (64 + 64) columns), so the tensor pipe runs S, dP of step
-// i+1 while the four warps turn S, dP of step i into P, dS; the accumulators take columns [256, 256 + 2 d).
+// Pipeline: warp 8 lane 0 = TMA producer (kStages ring of streamed tile pairs), warp 9 lane 0 = MMA issuer, warps 0-7 = two
+// threads per TMEM lane (warp w: lanes 32 (w % 4) .. + 31, columns 32 (w / 4) .. + 31 of S and dP — with one warp per scheduler
+// the element-wise pass ran at 0.3 instructions per cycle, bound by its own dependency latencies, and took longer than the
+// step's MMAs: profiles/r02_bwd_ncu_summary_v1.md).  S/dP are double-buffered in TMEM (2 x (64 + 64) columns), so the tensor
+// pipe runs S, dP of step i+1 while the eight warps turn S, dP of step i into P, dS; the accumulators take columns [256, 256 + 2 d).
 // The scale of dS (dS_raw = scale * P (dP - D)) is applied once, to the finished dQ / dK accumulators.
 #pragma once
 #include "fa_simt.cuh"   // ld_as_float
 #include "ptx.cuh"
+
+// -DFA_BWD_TRACE=1: CTA (0, 0, 0) records clock64() at the pipeline hand-offs of its first 32 steps into BwdParams::trace
+// ([role 0..3][step][slot 0..7]; roles: compute warp 0, compute warp 4, MMA thread, producer)
+#ifndef FA_BWD_TRACE
+#define FA_BWD_TRACE 0
+#endif
+#if FA_BWD_TRACE
+#define FA_BWD_TRACE_AT(role, step, slot)                                                                       \
+  do {                                                                                                           \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (step) < 32)             \
+      p.trace[((role) * 32 + (step)) * 8 + (slot)] = static_cast<unsigned long long>(clock64());                \
+  } while (0)
+#else
+#define FA_BWD_TRACE_AT(role, step, slot) do { } while (0)
+#endif
 
 namespace fa {
 
@@ -42,9 +59,11 @@ struct BwdParams {
   int64_t o0_sb, o0_sh, o0_sn;
   void* out1;         // kDKV: dK
   int64_t o1_sb, o1_sh, o1_sn;
+  unsigned long long* trace;   // FA_BWD_TRACE builds only; nullptr otherwise
 };
 
-constexpr int kBwdThreads = 192;   // 4 compute warps + producer warp + MMA warp
+constexpr int kBwdThreads = 320;   // 8 compute warps + producer warp + MMA warp
+constexpr int kBwdHalf = 32;       // S / dP columns per compute thread (two threads share a TMEM lane)
 constexpr int kBwdRes = 128;       // rows of a resident tile (keys of the dK/dV launch, query rows of the dQ launch)
 constexpr int kBwdStr = 64;        // rows of a streamed tile
 
@@ -117,7 +136,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
     n_steps = last < 0 ? 0 : last / kBwdStr + 1;
   }
 
-  if (warp == 5 && lane == 0) {
+  if (warp == 9 && lane == 0) {
     mbar_init(bar_res, 1);
     for (int i = 0; i < T::kStages; ++i) {
       mbar_init(bar_full + 8 * i, 1);
@@ -125,12 +144,12 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_s + 8 * b, 1);
-      mbar_init(bar_p + 8 * b, 128);
+      mbar_init(bar_p + 8 * b, 256);
     }
     mbar_init(bar_acc, 1);
     fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_r1);
       tma_prefetch_desc(&tm_r2);
@@ -146,7 +165,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem_ptr));
 
-  if (warp == 4) {
+  if (warp == 8) {
     // =========================== TMA producer ===========================
     if (lane == 0 && n_steps > 0) {
       mbar_arrive_expect_tx(bar_res, 2 * T::kResTileBytes);
@@ -158,6 +177,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
       for (int step = 0; step < n_steps; ++step) {
         const int st = step % T::kStages;
         if (step >= T::kStages) mbar_wait(bar_empty + 8 * st, ((step / T::kStages) - 1) & 1, TAG_B_EMPTY);
+        FA_BWD_TRACE_AT(3, step, 0);
         int head_t, srow;
         if (kDKV) {
           head_t = head_r * p.kv_group + step / per_head;
@@ -180,7 +200,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // =========================== MMA issuer ===========================
     if (lane == 0 && n_steps > 0) {
       constexpr uint32_t kFmt = kF16 ? 0u : 1u;
@@ -201,6 +221,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         const uint32_t b = static_cast<uint32_t>(step & 1);
         mbar_wait(bar_full + 8 * st, (step / T::kStages) & 1, TAG_B_FULL);
         tc_fence_after();
+        FA_BWD_TRACE_AT(2, step, 4);   // (row of the step whose S, dP are being issued)
         const uint64_t t1d = sdesc_at(hi_kmajor, sStage + st * T::kStageBytes);
         const uint64_t t2d = sdesc_at(hi_kmajor, sStage + st * T::kStageBytes + T::kStrTileBytes);
         const uint32_t dS = tmem_base + b * 128u;
@@ -220,37 +241,44 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
       };
       issue_sd(0);
       for (int step = 0; step < n_steps; ++step) {
+        FA_BWD_TRACE_AT(2, step, 0);
         if (step + 1 < n_steps) issue_sd(step + 1);
+        FA_BWD_TRACE_AT(2, step, 1);
         const int st = step % T::kStages;
         const uint32_t b = static_cast<uint32_t>(step & 1);
         mbar_wait(bar_p + 8 * b, (step >> 1) & 1, TAG_B_P);
         tc_fence_after();
+        FA_BWD_TRACE_AT(2, step, 2);
         const uint64_t t1m = sdesc_at(hi_mnmajor, sStage + st * T::kStageBytes);
         const uint64_t t2m = sdesc_at(hi_mnmajor, sStage + st * T::kStageBytes + T::kStrTileBytes);
-        const uint32_t aP = tmem_base + b * 128u;          // P (packed pairs) over the first 32 columns of S
-        const uint32_t aDS = tmem_base + b * 128u + 64u;   // dS over the first 32 columns of dP
+        // P / dS of streamed rows [32 h, 32 h + 32): packed pairs in columns [32 h, 32 h + 16) of S / dP; a k-step is 8 columns
+        const uint32_t aP = tmem_base + b * 128u;
+        const uint32_t aDS = tmem_base + b * 128u + 64u;
+        auto koff = [](int ks) { return static_cast<uint32_t>((ks >> 1) * kBwdHalf + (ks & 1) * 8); };
         const uint32_t acc0 = tmem_base + T::kTmemAcc;
         const uint32_t acc1 = acc0 + kHeadDim;
         if (kDKV) {
 #pragma unroll
           for (int ks = 0; ks < kKStepsR; ++ks)   // dV += P^T dO
-            mma_ts<false>(acc0, aP + ks * 8, t2m + static_cast<uint32_t>(ks * 128), idesc_acc, (step > 0 || ks > 0) ? 1u : 0u);
+            mma_ts<false>(acc0, aP + koff(ks), t2m + static_cast<uint32_t>(ks * 128), idesc_acc, (step > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
           for (int ks = 0; ks < kKStepsR; ++ks)   // dK += dS^T Q
-            mma_ts<false>(acc1, aDS + ks * 8, t1m + static_cast<uint32_t>(ks * 128), idesc_acc, (step > 0 || ks > 0) ? 1u : 0u);
+            mma_ts<false>(acc1, aDS + koff(ks), t1m + static_cast<uint32_t>(ks * 128), idesc_acc, (step > 0 || ks > 0) ? 1u : 0u);
         } else {
 #pragma unroll
           for (int ks = 0; ks < kKStepsR; ++ks)   // dQ += dS K
-            mma_ts<false>(acc0, aDS + ks * 8, t1m + static_cast<uint32_t>(ks * 128), idesc_acc, (step > 0 || ks > 0) ? 1u : 0u);
+            mma_ts<false>(acc0, aDS + koff(ks), t1m + static_cast<uint32_t>(ks * 128), idesc_acc, (step > 0 || ks > 0) ? 1u : 0u);
         }
         tc_commit(bar_empty + 8 * st);   // the stage's tiles (and this buffer's P, dS) have been read once these complete
+        FA_BWD_TRACE_AT(2, step, 3);
       }
       tc_commit(bar_acc);
     }
   } else {
-    // =========================== P, dS (one thread per TMEM lane) + epilogue ===========================
-    const int r = warp * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    // =========================== P, dS (two threads per TMEM lane) + epilogue ===========================
+    const int r = (warp & 3) * 32 + lane;
+    const int hh = warp >> 2;             // which half of the 64 columns of a step (and of the accumulator columns in the epilogue)
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int my_row = row0 + r;          // kDKV: key index    else: query row
     float l2r = INFINITY, dr = 0.f;       // dQ launch: the row's statistics
     if (!kDKV) {
@@ -265,15 +293,16 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
       if (kDKV) mbar_wait(bar_full + 8 * st, (step / T::kStages) & 1, TAG_B_FULL);   // the statistics of this stage
       mbar_wait(bar_s + 8 * b, (step >> 1) & 1, TAG_B_S);
       tc_fence_after();
+      const bool tracer = FA_BWD_TRACE && (warp & 3) == 0 && lane == 0;
+      if (tracer) FA_BWD_TRACE_AT(hh, step, 0);
       const uint32_t tS = tmem_base + lane_base + b * 128u;
       const uint32_t tDP = tS + 64u;
-      float s[64], dp[64];
-      tmem_ld32(tS, reinterpret_cast<uint32_t*>(&s[0]));
-      tmem_ld32(tS + 32, reinterpret_cast<uint32_t*>(&s[32]));
-      tmem_ld32(tDP, reinterpret_cast<uint32_t*>(&dp[0]));
-      tmem_ld32(tDP + 32, reinterpret_cast<uint32_t*>(&dp[32]));
+      float s[kBwdHalf], dp[kBwdHalf];
+      tmem_ld32(tS + hh * kBwdHalf, reinterpret_cast<uint32_t*>(&s[0]));
+      tmem_ld32(tDP + hh * kBwdHalf, reinterpret_cast<uint32_t*>(&dp[0]));
       tc_wait_ld();
-      // column c of this step is visible to this thread's row iff c_lo <= c <= c_hi
+      if (tracer) FA_BWD_TRACE_AT(hh, step, 1);
+      // column c (0 .. 63) of this step is visible to this thread's row iff c_lo <= c <= c_hi
       int c_lo = 0, c_hi = kBwdStr - 1;
       if (kDKV) {
         const int q0 = (i_first + step % per_head) * kBwdStr;
@@ -284,12 +313,14 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         c_hi = p.n_k - 1 - k0;
         if (p.causal) c_hi = min(c_hi, my_row + p.causal_offset - k0);
       }
-      const bool masked = c_lo > 0 || c_hi < kBwdStr - 1;
-      uint32_t ppk[32], dpk[32];
-      const uint32_t s_l2 = sStats + st * T::kStatsBytes;
+      c_lo -= hh * kBwdHalf;   // in this thread's own column numbering (0 .. 31)
+      c_hi -= hh * kBwdHalf;
+      const bool masked = c_lo > 0 || c_hi < kBwdHalf - 1;
+      uint32_t ppk[kBwdHalf / 2], dpk[kBwdHalf / 2];
+      const uint32_t s_l2 = sStats + st * T::kStatsBytes + hh * kBwdHalf * 4;
       const uint32_t s_d = s_l2 + kBwdStr * 4;
 #pragma unroll
-      for (int c4 = 0; c4 < kBwdStr / 4; ++c4) {
+      for (int c4 = 0; c4 < kBwdHalf / 4; ++c4) {
         float lq[4], dq[4];
         if (kDKV) {
           uint32_t a0, a1, a2, a3, d0, d1, d2, d3;
@@ -315,14 +346,19 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         dpk[c4 * 2] = pack_16x2<kF16>(dv[0], dv[1]);
         dpk[c4 * 2 + 1] = pack_16x2<kF16>(dv[2], dv[3]);
       }
-      if (kDKV) tmem_st32(tS, ppk);     // P^T over S (every S column is in registers by now)
-      tmem_st32(tDP, dpk);              // dS over dP
+      // P / dS (two 16-bit values per column) go over the first 16 of the thread's OWN 32 columns of S / dP, which it has in
+      // registers by now — the lane's other thread is never waited for
+      if (tracer) FA_BWD_TRACE_AT(hh, step, 2);
+      if (kDKV) tmem_st16(tS + hh * kBwdHalf, ppk);
+      tmem_st16(tDP + hh * kBwdHalf, dpk);
       tc_wait_st();
+      if (tracer) FA_BWD_TRACE_AT(hh, step, 3);
       tc_fence_before();
       mbar_arrive(bar_p + 8 * b);
+      if (tracer) FA_BWD_TRACE_AT(hh, step, 4);
     }
 
-    // ---- epilogue: accumulators -> (scale) -> 16-bit -> global, one row per thread ----
+    // ---- epilogue: accumulators -> (scale) -> 16-bit -> global, one row per pair of threads ----
     const bool have = n_steps > 0;
     if (have) {
       mbar_wait(bar_acc, 0, TAG_B_ACC);
@@ -332,7 +368,8 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
     auto store_acc = [&](uint32_t tcol, float mul, void* out, int64_t sb, int64_t sh, int64_t sn) {
       uint8_t* dst = static_cast<uint8_t*>(out) + 2 * (batch * sb + head_r * sh + static_cast<int64_t>(my_row) * sn);
 #pragma unroll
-      for (int cc = 0; cc < kHeadDim / 32; ++cc) {
+      for (int c2 = 0; c2 < kHeadDim / 64; ++c2) {
+        const int cc = hh * (kHeadDim / 64) + c2;   // 32-column chunk: thread hh of a lane takes columns [hh d/2, (hh + 1) d/2)
         uint32_t v[32];
         if (have) {
           tmem_ld32(tmem_base + lane_base + tcol + cc * 32, v);
