@@ -331,15 +331,11 @@ int run_bwd(const fa_bwd_params* p, cudaStream_t st) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
-  CUtensorMap q128, g128, k128, v128, q64, g64, k64, v64;
-  if ((rc = make_map(&k128, p->k, 2, dt, p->batch, kv_heads, p->n_k, p->head_dim, p->k_stride_b, p->k_stride_h, p->k_stride_n, sw, false, 128))) return rc;
-  if ((rc = make_map(&v128, p->v, 2, dt, p->batch, kv_heads, p->n_k, p->head_dim, p->v_stride_b, p->v_stride_h, p->v_stride_n, sw, false, 128))) return rc;
-  if ((rc = make_map(&q64, p->q, 2, dt, p->batch, p->heads, p->n_q, p->head_dim, p->q_stride_b, p->q_stride_h, p->q_stride_n, sw, false, 64))) return rc;
-  if ((rc = make_map(&g64, p->d_o, 2, dt, p->batch, p->heads, p->n_q, p->head_dim, p->do_stride_b, p->do_stride_h, p->do_stride_n, sw, false, 64))) return rc;
-  if ((rc = make_map(&q128, p->q, 2, dt, p->batch, p->heads, p->n_q, p->head_dim, p->q_stride_b, p->q_stride_h, p->q_stride_n, sw, false, 128))) return rc;
-  if ((rc = make_map(&g128, p->d_o, 2, dt, p->batch, p->heads, p->n_q, p->head_dim, p->do_stride_b, p->do_stride_h, p->do_stride_n, sw, false, 128))) return rc;
-  if ((rc = make_map(&k64, p->k, 2, dt, p->batch, kv_heads, p->n_k, p->head_dim, p->k_stride_b, p->k_stride_h, p->k_stride_n, sw, false, 64))) return rc;
-  if ((rc = make_map(&v64, p->v, 2, dt, p->batch, kv_heads, p->n_k, p->head_dim, p->v_stride_b, p->v_stride_h, p->v_stride_n, sw, false, 64))) return rc;
+  CUtensorMap mq, mg, mk, mv;   // one box shape (128 rows x 128 bytes) serves the resident and the streamed role of each tensor
+  if ((rc = make_map(&mq, p->q, 2, dt, p->batch, p->heads, p->n_q, p->head_dim, p->q_stride_b, p->q_stride_h, p->q_stride_n, sw))) return rc;
+  if ((rc = make_map(&mg, p->d_o, 2, dt, p->batch, p->heads, p->n_q, p->head_dim, p->do_stride_b, p->do_stride_h, p->do_stride_n, sw))) return rc;
+  if ((rc = make_map(&mk, p->k, 2, dt, p->batch, kv_heads, p->n_k, p->head_dim, p->k_stride_b, p->k_stride_h, p->k_stride_n, sw))) return rc;
+  if ((rc = make_map(&mv, p->v, 2, dt, p->batch, kv_heads, p->n_k, p->head_dim, p->v_stride_b, p->v_stride_h, p->v_stride_n, sw))) return rc;
   fa::BwdParams bp;
   memset(&bp, 0, sizeof(bp));
   bp.scale = p->scale;
@@ -384,7 +380,7 @@ int run_bwd(const fa_bwd_params* p, cudaStream_t st) {
     if (btrace_path && !btrace_dq) b.trace = d_btrace;
 #endif
     const dim3 grid((unsigned)((p->n_k + 127) / 128), (unsigned)kv_heads, (unsigned)p->batch);
-    if ((rc = launch_bwd_d<true>(di, f16, k128, v128, q64, g64, b, grid, st))) return rc;
+    if ((rc = launch_bwd_d<true>(di, f16, mk, mv, mq, mg, b, grid, st))) return rc;
   }
   {   // dQ: one CTA per 128 query rows of a head
     fa::BwdParams b = bp;
@@ -393,7 +389,7 @@ int run_bwd(const fa_bwd_params* p, cudaStream_t st) {
     if (btrace_path && btrace_dq) b.trace = d_btrace;
 #endif
     const dim3 grid((unsigned)((p->n_q + 127) / 128), (unsigned)p->heads, (unsigned)p->batch);
-    if ((rc = launch_bwd_d<false>(di, f16, q128, g128, k64, v64, b, grid, st))) return rc;
+    if ((rc = launch_bwd_d<false>(di, f16, mq, mg, mk, mv, b, grid, st))) return rc;
   }
   return FA_OK;
 }

@@ -3,11 +3,11 @@
 // it leaves open); SURVEY §8 (f4) names the backward pass as the widening step after the forward rows.
 //
 // Two launches of ONE kernel template, both atomics-free and deterministic:
-//   kDKV = true   a CTA owns 128 keys of one K/V head (resident tiles K_j, V_j) and streams 64-row tiles of (Q, dO) of every
+//   kDKV = true   a CTA owns 128 keys of one K/V head (resident tiles K_j, V_j) and streams 128-row tiles of (Q, dO) of every
 //                 query head of its group:   S^T = K Q^T,  dP^T = V dO^T   (tcgen05.mma, A and B from SMEM, D in TMEM)
 //                 P^T = exp2(S^T c - LSE2[q]),  dS^T = P^T (dP^T - D[q])   (one thread per key row, statistics per column)
 //                 dV += P^T dO,  dK += dS^T Q                              (A = P^T / dS^T read straight from TMEM)
-//   kDKV = false  a CTA owns 128 query rows of one head (resident Q_i, dO_i) and streams 64-key tiles of (K, V):
+//   kDKV = false  a CTA owns 128 query rows of one head (resident Q_i, dO_i) and streams 128-key tiles of (K, V):
 //                 S = Q K^T,  dP = dO V^T,  dS = P (dP - D[q])  (statistics per row, in registers),  dQ += dS K
 // i.e. 4 + 3 = 7 contractions instead of the 5 of a single-pass backward: recomputing S and dP in the second launch is what
 // buys the absence of a dQ reduction across CTAs (no atomics, no dQ workspace, bit-reproducible results), and every
@@ -18,11 +18,15 @@
 // D[q] = rowsum(dO * O) and LSE2[q] = LSE * log2(e) come from fa_bwd_prep_kernel in a workspace whose rows are padded to a
 // multiple of 128 per (batch, head) (+inf / 0 in the padding and for rows that saw no key: P = exp2(x - inf) = 0 there).
 //
-// Pipeline: warp 8 lane 0 = TMA producer (kStages ring of streamed tile pairs), warp 9 lane 0 = MMA issuer, warps 0-7 = two
-// threads per TMEM lane (warp w: lanes 32 (w % 4) .. + 31, columns 32 (w / 4) .. + 31 of S and dP — with one warp per scheduler
-// the element-wise pass ran at 0.3 instructions per cycle, bound by its own dependency latencies, and took longer than the
-// step's MMAs: profiles/r02_bwd_ncu_summary_v1.md).  S/dP are double-buffered in TMEM (2 x (64 + 64) columns), so the tensor
-// pipe runs S, dP of step i+1 while the eight warps turn S, dP of step i into P, dS; the accumulators take columns [256, 256 + 2 d).
+// Pipeline: warp 8 lane 0 = TMA producer (ring of streamed tile pairs), warp 9 lane 0 = MMA issuer, warps 0-7 = two threads per
+// TMEM lane (warp w: lanes 32 (w % 4) .. + 31, columns 64 (w / 4) .. + 63 of S and dP).  Streamed tiles are 128 rows: every
+// contraction is then a run of eight 128 x 128 x 16 MMAs at the full tensor rate (64-row tiles were measured first: their
+// 128 x 64 MMAs cost 54 instead of 33.5 cycles per 64 columns, and the fixed costs per step — barrier waits, the switch between
+// SMEM- and TMEM-sourced MMAs — weigh twice as much: profiles/r02_bwd_trace_v2_8warps.txt).  TMEM is exactly full at d = 128
+// (S 128 + dP 128 + two accumulators), so S and dP cannot be double-buffered; instead the two regions alternate: the tensor
+// pipe runs   [P(i)] dV(i), S(i+1), [dS(i)] dK(i), dP(i+1)   — while the warps compute P(i) from S(i) it runs dK(i-1) and dP(i),
+// while they compute dS(i) from dP(i) it runs dV(i) and S(i+1).  P^T / dS^T (packed 16-bit pairs) overwrite the first half of
+// each thread's own S / dP columns.
 // The scale of dS (dS_raw = scale * P (dP - D)) is applied once, to the finished dQ / dK accumulators.
 #pragma once
 #include "fa_simt.cuh"   // ld_as_float
@@ -63,29 +67,28 @@ struct BwdParams {
 };
 
 constexpr int kBwdThreads = 320;   // 8 compute warps + producer warp + MMA warp
-constexpr int kBwdHalf = 32;       // S / dP columns per compute thread (two threads share a TMEM lane)
 constexpr int kBwdRes = 128;       // rows of a resident tile (keys of the dK/dV launch, query rows of the dQ launch)
-constexpr int kBwdStr = 64;        // rows of a streamed tile
+constexpr int kBwdStr = 128;       // rows of a streamed tile
+constexpr int kBwdHalf = 64;       // S / dP columns per compute thread (two threads share a TMEM lane)
 
 template <int kHeadDim>
 struct BwdTraits {
   static_assert(kHeadDim == 64 || kHeadDim == 128, "backward instances: 128- and 256-byte rows of 16-bit elements");
   static constexpr int kDChunks = kHeadDim * 2 / 128;            // 128-byte column chunks per row
-  static constexpr int kResChunkBytes = kBwdRes * 128;           // one TMA box of a resident tile
-  static constexpr int kStrChunkBytes = kBwdStr * 128;           // one TMA box of a streamed tile
-  static constexpr int kResTileBytes = kDChunks * kResChunkBytes;
-  static constexpr int kStrTileBytes = kDChunks * kStrChunkBytes;
-  static constexpr int kStageBytes = 2 * kStrTileBytes;          // the streamed pair
-  static constexpr int kStages = kDChunks == 1 ? 6 : 4;
-  static constexpr int kStatsBytes = 2 * kBwdStr * 4;            // LSE2[64] | D[64] of a streamed (Q, dO) tile
-  static constexpr int kNumBarriers = 1 + 2 * kStages + 2 + 2 + 1;
-  static constexpr int kSmemBytes = 2 * kResTileBytes + kStages * (kStageBytes + kStatsBytes) + kNumBarriers * 8 + 16 + 1024;
+  static constexpr int kChunkBytes = 128 * 128;                  // one TMA box: 128 rows x 128 bytes
+  static constexpr int kTileBytes = kDChunks * kChunkBytes;      // resident and streamed tiles alike
+  static constexpr int kStageBytes = 2 * kTileBytes;             // the streamed pair
+  static constexpr int kStages = kDChunks == 1 ? 4 : 2;
+  static constexpr int kStatsBytes = 2 * kBwdStr * 4;            // LSE2[128] | D[128] of a streamed (Q, dO) tile
+  static constexpr int kNumBarriers = 1 + 2 * kStages + 4 + 1;
+  static constexpr int kSmemBytes = 2 * kTileBytes + kStages * (kStageBytes + kStatsBytes) + kNumBarriers * 8 + 16 + 1024;
+  static constexpr int kTmemS = 0, kTmemDP = 128;                // S and dP: 128 fp32 columns each (P / dS alias them)
   static constexpr int kTmemAcc = 256;                           // acc0 at 256, acc1 at 256 + kHeadDim
   static_assert(kTmemAcc + 2 * kHeadDim <= 512, "TMEM budget");
   static_assert(kSmemBytes <= 227 * 1024, "SMEM budget");
 };
 
-enum : uint32_t { TAG_B_RES = 21, TAG_B_FULL = 22, TAG_B_EMPTY = 23, TAG_B_S = 24, TAG_B_P = 25, TAG_B_ACC = 26 };
+enum : uint32_t { TAG_B_RES = 21, TAG_B_FULL = 22, TAG_B_EMPTY = 23, TAG_B_S = 24, TAG_B_P = 25, TAG_B_ACC = 26, TAG_B_DP = 27, TAG_B_DS = 28 };
 
 // plain (non-tensor) bulk copy global -> shared, completing on an mbarrier; 16-byte aligned on both sides, bytes % 16 == 0
 FA_DEVINL void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
@@ -102,15 +105,17 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
   extern __shared__ uint8_t bwd_smem_raw[];
   const uint32_t smem0 = (smem_u32(bwd_smem_raw) + 1023u) & ~1023u;
   const uint32_t sR1 = smem0;                                      // kDKV: K_j    else: Q_i
-  const uint32_t sR2 = sR1 + T::kResTileBytes;                     // kDKV: V_j    else: dO_i
-  const uint32_t sStage = sR2 + T::kResTileBytes;                  // [kStages][t1 | t2]   kDKV: (Q, dO)   else: (K, V)
-  const uint32_t sStats = sStage + T::kStages * T::kStageBytes;    // [kStages][LSE2[64] | D[64]]  (kDKV)
+  const uint32_t sR2 = sR1 + T::kTileBytes;                        // kDKV: V_j    else: dO_i
+  const uint32_t sStage = sR2 + T::kTileBytes;                     // [kStages][t1 | t2]   kDKV: (Q, dO)   else: (K, V)
+  const uint32_t sStats = sStage + T::kStages * T::kStageBytes;    // [kStages][LSE2[128] | D[128]]  (kDKV)
   const uint32_t bar_res = sStats + T::kStages * T::kStatsBytes;
   const uint32_t bar_full = bar_res + 8;                           // [kStages]
   const uint32_t bar_empty = bar_full + 8 * T::kStages;            // [kStages]
-  const uint32_t bar_s = bar_empty + 8 * T::kStages;               // [2]  S, dP of TMEM buffer b complete
-  const uint32_t bar_p = bar_s + 16;                               // [2]  P, dS of TMEM buffer b written
-  const uint32_t bar_acc = bar_p + 16;                             // accumulators final
+  const uint32_t bar_s = bar_empty + 8 * T::kStages;               // S of the step complete
+  const uint32_t bar_dp = bar_s + 8;                               // dP of the step complete
+  const uint32_t bar_p = bar_dp + 8;                               // kDKV: P written over S   else: S is in registers (its columns are free)
+  const uint32_t bar_ds = bar_p + 8;                               // dS written over dP
+  const uint32_t bar_acc = bar_ds + 8;                             // accumulators final
   const uint32_t s_tmem_ptr = bar_acc + 8;
 
   const int warp = threadIdx.x >> 5;
@@ -122,13 +127,13 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
   const int row0 = tile * kBwdRes;
 
   // ---- the streamed steps of this CTA ----
-  // kDKV: step -> (g, i): query head head_r * kv_group + g, rows [64 i, 64 i + 64), i from the first tile with a row that sees
-  //       one of this CTA's keys.  else: step j -> keys [64 j, 64 j + 64), up to the last key any of the CTA's rows sees.
+  // kDKV: step -> (g, i): query head head_r * kv_group + g, rows [128 i, 128 i + 128), i from the first tile with a row that
+  //       sees one of this CTA's keys.  else: step j -> keys [128 j, 128 j + 128), up to the last key any of the CTA's rows sees.
   int i_first = 0, per_head = 0, n_steps = 0;
   if (kDKV) {
-    const int nq64 = (p.n_q + kBwdStr - 1) / kBwdStr;
+    const int nq_t = (p.n_q + kBwdStr - 1) / kBwdStr;
     if (p.causal) i_first = max(0, row0 - p.causal_offset) / kBwdStr;
-    per_head = max(0, nq64 - i_first);
+    per_head = max(0, nq_t - i_first);
     n_steps = per_head * p.kv_group;
   } else {
     int last = p.n_k - 1;
@@ -142,10 +147,10 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
       mbar_init(bar_full + 8 * i, 1);
       mbar_init(bar_empty + 8 * i, 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_s + 8 * b, 1);
-      mbar_init(bar_p + 8 * b, 256);
-    }
+    mbar_init(bar_s, 1);
+    mbar_init(bar_dp, 1);
+    mbar_init(bar_p, 256);
+    mbar_init(bar_ds, 256);
     mbar_init(bar_acc, 1);
     fence_mbar_init();
   }
@@ -168,11 +173,11 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
   if (warp == 8) {
     // =========================== TMA producer ===========================
     if (lane == 0 && n_steps > 0) {
-      mbar_arrive_expect_tx(bar_res, 2 * T::kResTileBytes);
+      mbar_arrive_expect_tx(bar_res, 2 * T::kTileBytes);
 #pragma unroll
       for (int c = 0; c < T::kDChunks; ++c) {
-        tma_load_4d(sR1 + c * T::kResChunkBytes, &tm_r1, bar_res, c * 64, row0, head_r, batch);
-        tma_load_4d(sR2 + c * T::kResChunkBytes, &tm_r2, bar_res, c * 64, row0, head_r, batch);
+        tma_load_4d(sR1 + c * T::kChunkBytes, &tm_r1, bar_res, c * 64, row0, head_r, batch);
+        tma_load_4d(sR2 + c * T::kChunkBytes, &tm_r2, bar_res, c * 64, row0, head_r, batch);
       }
       for (int step = 0; step < n_steps; ++step) {
         const int st = step % T::kStages;
@@ -190,8 +195,8 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         mbar_arrive_expect_tx(bar_full + 8 * st, T::kStageBytes + (kDKV ? T::kStatsBytes : 0));
 #pragma unroll
         for (int c = 0; c < T::kDChunks; ++c) {
-          tma_load_4d(dst + c * T::kStrChunkBytes, &tm_t1, bar_full + 8 * st, c * 64, srow, head_t, batch);
-          tma_load_4d(dst + T::kStrTileBytes + c * T::kStrChunkBytes, &tm_t2, bar_full + 8 * st, c * 64, srow, head_t, batch);
+          tma_load_4d(dst + c * T::kChunkBytes, &tm_t1, bar_full + 8 * st, c * 64, srow, head_t, batch);
+          tma_load_4d(dst + T::kTileBytes + c * T::kChunkBytes, &tm_t2, bar_full + 8 * st, c * 64, srow, head_t, batch);
         }
         if (kDKV) {
           const int64_t off = (static_cast<int64_t>(batch) * p.heads + head_t) * p.n_q_pad + srow;
@@ -202,82 +207,81 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
     }
   } else if (warp == 9) {
     // =========================== MMA issuer ===========================
+    // Order on the (in-order) tensor pipe:  S(0) dP(0) | then per step i:  [P(i)] dV(i)  S(i+1)  [dS(i)] dK(i)  dP(i+1)
+    // (dQ launch: no dV; dK -> dQ).  S(i+1) overwrites the S columns once dV(i) has read P(i) out of them, dP(i+1) the dP columns
+    // once dK(i) has read dS(i): the two 128-column regions are the double buffer, one contraction apart.
     if (lane == 0 && n_steps > 0) {
       constexpr uint32_t kFmt = kF16 ? 0u : 1u;
-      constexpr uint32_t idesc_sd = make_idesc(kFmt, 0, kBwdRes, kBwdStr);      // S, dP: 128 x 64, both operands K-major
+      constexpr uint32_t idesc_sd = make_idesc(kFmt, 0, kBwdRes, kBwdStr);      // S, dP: 128 x 128, both operands K-major
       constexpr uint32_t idesc_acc = make_idesc(kFmt, 1, kBwdRes, kHeadDim);    // accumulators: 128 x d, B MN-major
       constexpr uint64_t hi_kmajor = make_sdesc_hi_sw128(16, 1024);
-      // a streamed tile as the MN-major B operand (N = d, K = its 64 rows): LBO = stride between the 128-byte column chunks,
+      // a streamed tile as the MN-major B operand (N = d, K = its 128 rows): LBO = stride between the 128-byte column chunks,
       // SBO = stride between 8-row groups
-      constexpr uint64_t hi_mnmajor = make_sdesc_hi_sw128(T::kStrChunkBytes, 1024);
+      constexpr uint64_t hi_mnmajor = make_sdesc_hi_sw128(T::kChunkBytes, 1024);
       constexpr int kKStepsD = kHeadDim / 16;       // k-steps over the head dim (S, dP)
       constexpr int kKStepsR = kBwdStr / 16;        // k-steps over the streamed rows (accumulators)
       mbar_wait(bar_res, 0, TAG_B_RES);
       tc_fence_after();
       const uint64_t r1d = sdesc_at(hi_kmajor, sR1);
       const uint64_t r2d = sdesc_at(hi_kmajor, sR2);
-      auto issue_sd = [&](int step) {
-        const int st = step % T::kStages;
-        const uint32_t b = static_cast<uint32_t>(step & 1);
-        mbar_wait(bar_full + 8 * st, (step / T::kStages) & 1, TAG_B_FULL);
+      const uint32_t tS = tmem_base + T::kTmemS, tDP = tmem_base + T::kTmemDP;
+      const uint32_t acc0 = tmem_base + T::kTmemAcc, acc1 = acc0 + kHeadDim;
+      auto wait_full = [&](int step) {
+        mbar_wait(bar_full + 8 * (step % T::kStages), (step / T::kStages) & 1, TAG_B_FULL);
         tc_fence_after();
-        FA_BWD_TRACE_AT(2, step, 4);   // (row of the step whose S, dP are being issued)
-        const uint64_t t1d = sdesc_at(hi_kmajor, sStage + st * T::kStageBytes);
-        const uint64_t t2d = sdesc_at(hi_kmajor, sStage + st * T::kStageBytes + T::kStrTileBytes);
-        const uint32_t dS = tmem_base + b * 128u;
-#pragma unroll
-        for (int kk = 0; kk < kKStepsD; ++kk) {
-          const uint32_t offr = ((kk >> 2) * T::kResChunkBytes + (kk & 3) * 32) >> 4;
-          const uint32_t offt = ((kk >> 2) * T::kStrChunkBytes + (kk & 3) * 32) >> 4;
-          mma_ss<false>(dS, r1d + offr, t1d + offt, idesc_sd, kk > 0 ? 1u : 0u);
-        }
-#pragma unroll
-        for (int kk = 0; kk < kKStepsD; ++kk) {
-          const uint32_t offr = ((kk >> 2) * T::kResChunkBytes + (kk & 3) * 32) >> 4;
-          const uint32_t offt = ((kk >> 2) * T::kStrChunkBytes + (kk & 3) * 32) >> 4;
-          mma_ss<false>(dS + 64u, r2d + offr, t2d + offt, idesc_sd, kk > 0 ? 1u : 0u);
-        }
-        tc_commit(bar_s + 8 * b);
       };
-      issue_sd(0);
-      for (int step = 0; step < n_steps; ++step) {
-        FA_BWD_TRACE_AT(2, step, 0);
-        if (step + 1 < n_steps) issue_sd(step + 1);
-        FA_BWD_TRACE_AT(2, step, 1);
-        const int st = step % T::kStages;
-        const uint32_t b = static_cast<uint32_t>(step & 1);
-        mbar_wait(bar_p + 8 * b, (step >> 1) & 1, TAG_B_P);
-        tc_fence_after();
-        FA_BWD_TRACE_AT(2, step, 2);
-        const uint64_t t1m = sdesc_at(hi_mnmajor, sStage + st * T::kStageBytes);
-        const uint64_t t2m = sdesc_at(hi_mnmajor, sStage + st * T::kStageBytes + T::kStrTileBytes);
-        // P / dS of streamed rows [32 h, 32 h + 32): packed pairs in columns [32 h, 32 h + 16) of S / dP; a k-step is 8 columns
-        const uint32_t aP = tmem_base + b * 128u;
-        const uint32_t aDS = tmem_base + b * 128u + 64u;
-        auto koff = [](int ks) { return static_cast<uint32_t>((ks >> 1) * kBwdHalf + (ks & 1) * 8); };
-        const uint32_t acc0 = tmem_base + T::kTmemAcc;
-        const uint32_t acc1 = acc0 + kHeadDim;
-        if (kDKV) {
+      // D[tmem d] = R (resident, K-major) x T^T (streamed tile `which` of the step's stage, K-major)
+      auto issue_rt = [&](uint32_t d, uint64_t rd, int step, int which) {
+        const uint64_t td = sdesc_at(hi_kmajor, sStage + (step % T::kStages) * T::kStageBytes + which * T::kTileBytes);
 #pragma unroll
-          for (int ks = 0; ks < kKStepsR; ++ks)   // dV += P^T dO
-            mma_ts<false>(acc0, aP + koff(ks), t2m + static_cast<uint32_t>(ks * 128), idesc_acc, (step > 0 || ks > 0) ? 1u : 0u);
-#pragma unroll
-          for (int ks = 0; ks < kKStepsR; ++ks)   // dK += dS^T Q
-            mma_ts<false>(acc1, aDS + koff(ks), t1m + static_cast<uint32_t>(ks * 128), idesc_acc, (step > 0 || ks > 0) ? 1u : 0u);
-        } else {
-#pragma unroll
-          for (int ks = 0; ks < kKStepsR; ++ks)   // dQ += dS K
-            mma_ts<false>(acc0, aDS + koff(ks), t1m + static_cast<uint32_t>(ks * 128), idesc_acc, (step > 0 || ks > 0) ? 1u : 0u);
+        for (int kk = 0; kk < kKStepsD; ++kk) {
+          const uint32_t off = ((kk >> 2) * T::kChunkBytes + (kk & 3) * 32) >> 4;
+          mma_ss<false>(d, rd + off, td + off, idesc_sd, kk > 0 ? 1u : 0u);
         }
-        tc_commit(bar_empty + 8 * st);   // the stage's tiles (and this buffer's P, dS) have been read once these complete
+      };
+      // acc += A (TMEM: packed P or dS, streamed rows [64 h, 64 h + 64) in columns [64 h, 64 h + 32) of its region) x T (MN-major)
+      auto issue_acc = [&](uint32_t acc, uint32_t a, int step, int which) {
+        const uint64_t tm = sdesc_at(hi_mnmajor, sStage + (step % T::kStages) * T::kStageBytes + which * T::kTileBytes);
+#pragma unroll
+        for (int ks = 0; ks < kKStepsR; ++ks)
+          mma_ts<false>(acc, a + static_cast<uint32_t>((ks >> 2) * kBwdHalf + (ks & 3) * 8), tm + static_cast<uint32_t>(ks * 128), idesc_acc,
+                        (step > 0 || ks > 0) ? 1u : 0u);
+      };
+      wait_full(0);
+      issue_rt(tS, r1d, 0, 0);
+      tc_commit(bar_s);
+      issue_rt(tDP, r2d, 0, 1);
+      tc_commit(bar_dp);
+      for (int step = 0; step < n_steps; ++step) {
+        const uint32_t par = static_cast<uint32_t>(step & 1);
+        FA_BWD_TRACE_AT(2, step, 0);
+        mbar_wait(bar_p, par, TAG_B_P);
+        tc_fence_after();
+        FA_BWD_TRACE_AT(2, step, 1);
+        if (kDKV) issue_acc(acc0, tS, step, 1);            // dV += P^T dO
+        if (step + 1 < n_steps) {
+          wait_full(step + 1);
+          issue_rt(tS, r1d, step + 1, 0);                  // S of the next step
+          tc_commit(bar_s);
+        }
+        FA_BWD_TRACE_AT(2, step, 2);
+        mbar_wait(bar_ds, par, TAG_B_DS);
+        tc_fence_after();
         FA_BWD_TRACE_AT(2, step, 3);
+        issue_acc(kDKV ? acc1 : acc0, tDP, step, 0);       // dK += dS^T Q   /   dQ += dS K
+        tc_commit(bar_empty + 8 * (step % T::kStages));    // the stage's tiles have been read once everything issued so far completes
+        if (step + 1 < n_steps) {
+          issue_rt(tDP, r2d, step + 1, 1);                 // dP of the next step
+          tc_commit(bar_dp);
+        }
+        FA_BWD_TRACE_AT(2, step, 4);
       }
       tc_commit(bar_acc);
     }
   } else {
     // =========================== P, dS (two threads per TMEM lane) + epilogue ===========================
     const int r = (warp & 3) * 32 + lane;
-    const int hh = warp >> 2;             // which half of the 64 columns of a step (and of the accumulator columns in the epilogue)
+    const int hh = warp >> 2;             // which half of the 128 columns of a step (and of the accumulator columns in the epilogue)
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int my_row = row0 + r;          // kDKV: key index    else: query row
     float l2r = INFINITY, dr = 0.f;       // dQ launch: the row's statistics
@@ -287,22 +291,13 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
       dr = p.dsum[off];
     }
     const bool row_valid = kDKV ? (my_row < p.n_k) : true;   // (query rows beyond n_q have LSE2 = +inf)
+    const uint32_t tS = tmem_base + lane_base + T::kTmemS + hh * kBwdHalf;     // this thread's 64 columns of S ...
+    const uint32_t tDP = tmem_base + lane_base + T::kTmemDP + hh * kBwdHalf;   // ... and of dP
+    const bool tracer = FA_BWD_TRACE && (warp & 3) == 0 && lane == 0;
     for (int step = 0; step < n_steps; ++step) {
       const int st = step % T::kStages;
-      const uint32_t b = static_cast<uint32_t>(step & 1);
-      if (kDKV) mbar_wait(bar_full + 8 * st, (step / T::kStages) & 1, TAG_B_FULL);   // the statistics of this stage
-      mbar_wait(bar_s + 8 * b, (step >> 1) & 1, TAG_B_S);
-      tc_fence_after();
-      const bool tracer = FA_BWD_TRACE && (warp & 3) == 0 && lane == 0;
-      if (tracer) FA_BWD_TRACE_AT(hh, step, 0);
-      const uint32_t tS = tmem_base + lane_base + b * 128u;
-      const uint32_t tDP = tS + 64u;
-      float s[kBwdHalf], dp[kBwdHalf];
-      tmem_ld32(tS + hh * kBwdHalf, reinterpret_cast<uint32_t*>(&s[0]));
-      tmem_ld32(tDP + hh * kBwdHalf, reinterpret_cast<uint32_t*>(&dp[0]));
-      tc_wait_ld();
-      if (tracer) FA_BWD_TRACE_AT(hh, step, 1);
-      // column c (0 .. 63) of this step is visible to this thread's row iff c_lo <= c <= c_hi
+      const uint32_t par = static_cast<uint32_t>(step & 1);
+      // column c (0 .. 127) of this step is visible to this thread's row iff c_lo <= c <= c_hi; then in its own numbering (0 .. 63)
       int c_lo = 0, c_hi = kBwdStr - 1;
       if (kDKV) {
         const int q0 = (i_first + step % per_head) * kBwdStr;
@@ -313,48 +308,90 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         c_hi = p.n_k - 1 - k0;
         if (p.causal) c_hi = min(c_hi, my_row + p.causal_offset - k0);
       }
-      c_lo -= hh * kBwdHalf;   // in this thread's own column numbering (0 .. 31)
+      c_lo -= hh * kBwdHalf;
       c_hi -= hh * kBwdHalf;
       const bool masked = c_lo > 0 || c_hi < kBwdHalf - 1;
-      uint32_t ppk[kBwdHalf / 2], dpk[kBwdHalf / 2];
       const uint32_t s_l2 = sStats + st * T::kStatsBytes + hh * kBwdHalf * 4;
       const uint32_t s_d = s_l2 + kBwdStr * 4;
+      if (kDKV) mbar_wait(bar_full + 8 * st, (step / T::kStages) & 1, TAG_B_FULL);   // the statistics of this stage
+
+      // ---- P = exp2(S c - LSE2) ----
+      mbar_wait(bar_s, par, TAG_B_S);
+      tc_fence_after();
+      if (tracer) FA_BWD_TRACE_AT(hh, step, 0);
+      float pr[kBwdHalf];
+      tmem_ld32(tS, reinterpret_cast<uint32_t*>(&pr[0]));
+      tmem_ld32(tS + 32, reinterpret_cast<uint32_t*>(&pr[32]));
+      tc_wait_ld();
+      if (!kDKV) {   // S is in registers and nothing is written back over it: the next S may be issued
+        tc_fence_before();
+        mbar_arrive(bar_p);
+      }
 #pragma unroll
       for (int c4 = 0; c4 < kBwdHalf / 4; ++c4) {
-        float lq[4], dq[4];
+        float lq[4];
         if (kDKV) {
-          uint32_t a0, a1, a2, a3, d0, d1, d2, d3;
+          uint32_t a0, a1, a2, a3;
           ld_shared_v4(s_l2 + c4 * 16, a0, a1, a2, a3);
-          ld_shared_v4(s_d + c4 * 16, d0, d1, d2, d3);
           lq[0] = __uint_as_float(a0); lq[1] = __uint_as_float(a1); lq[2] = __uint_as_float(a2); lq[3] = __uint_as_float(a3);
-          dq[0] = __uint_as_float(d0); dq[1] = __uint_as_float(d1); dq[2] = __uint_as_float(d2); dq[3] = __uint_as_float(d3);
         } else {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) { lq[u] = l2r; dq[u] = dr; }
+          for (int u = 0; u < 4; ++u) lq[u] = l2r;
         }
-        float pv[4], dv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int c = c4 * 4 + u;
-          float e = ex2(fmaf(s[c], p.scale_log2, -lq[u]));
+          float e = ex2(fmaf(pr[c], p.scale_log2, -lq[u]));
           if (masked && (c < c_lo || c > c_hi)) e = 0.f;
-          pv[u] = e;
-          dv[u] = e * (dp[c] - dq[u]);
+          pr[c] = e;
         }
-        ppk[c4 * 2] = pack_16x2<kF16>(pv[0], pv[1]);
-        ppk[c4 * 2 + 1] = pack_16x2<kF16>(pv[2], pv[3]);
-        dpk[c4 * 2] = pack_16x2<kF16>(dv[0], dv[1]);
-        dpk[c4 * 2 + 1] = pack_16x2<kF16>(dv[2], dv[3]);
       }
-      // P / dS (two 16-bit values per column) go over the first 16 of the thread's OWN 32 columns of S / dP, which it has in
-      // registers by now — the lane's other thread is never waited for
+      if (tracer) FA_BWD_TRACE_AT(hh, step, 1);
+      if (kDKV) {
+        // P^T (two 16-bit values per column) goes over the first 32 of the thread's OWN 64 columns of S, which it has in registers
+        uint32_t pk[kBwdHalf / 2];
+#pragma unroll
+        for (int i = 0; i < kBwdHalf / 2; ++i) pk[i] = pack_16x2<kF16>(pr[2 * i], pr[2 * i + 1]);
+        tmem_st32(tS, pk);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_p);
+      }
       if (tracer) FA_BWD_TRACE_AT(hh, step, 2);
-      if (kDKV) tmem_st16(tS + hh * kBwdHalf, ppk);
-      tmem_st16(tDP + hh * kBwdHalf, dpk);
-      tc_wait_st();
+
+      // ---- dS = P (dP - D) ----
+      mbar_wait(bar_dp, par, TAG_B_DP);
+      tc_fence_after();
       if (tracer) FA_BWD_TRACE_AT(hh, step, 3);
+      uint32_t dk[kBwdHalf / 2];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {   // in two pieces of 32 columns: 32 live dP registers instead of 64
+        float dp[32];
+        tmem_ld32(tDP + h2 * 32, reinterpret_cast<uint32_t*>(&dp[0]));
+        tc_wait_ld();
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float dq[4];
+          if (kDKV) {
+            uint32_t d0, d1, d2, d3;
+            ld_shared_v4(s_d + (h2 * 8 + c4) * 16, d0, d1, d2, d3);
+            dq[0] = __uint_as_float(d0); dq[1] = __uint_as_float(d1); dq[2] = __uint_as_float(d2); dq[3] = __uint_as_float(d3);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dq[u] = dr;
+          }
+          float dv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dv[u] = pr[h2 * 32 + c4 * 4 + u] * (dp[c4 * 4 + u] - dq[u]);
+          dk[h2 * 16 + c4 * 2] = pack_16x2<kF16>(dv[0], dv[1]);
+          dk[h2 * 16 + c4 * 2 + 1] = pack_16x2<kF16>(dv[2], dv[3]);
+        }
+      }
+      // dS over the first 32 of the thread's own 64 columns of dP (all 64 are in registers by now)
+      tmem_st32(tDP, dk);
+      tc_wait_st();
       tc_fence_before();
-      mbar_arrive(bar_p + 8 * b);
+      mbar_arrive(bar_ds);
       if (tracer) FA_BWD_TRACE_AT(hh, step, 4);
     }
 
@@ -405,7 +442,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     __syncwarp();
     tmem_dealloc(tmem_base, 512);
   }
