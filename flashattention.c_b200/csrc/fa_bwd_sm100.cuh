@@ -29,6 +29,8 @@
 // each thread's own S / dP columns.
 // The scale of dS (dS_raw = scale * P (dP - D)) is applied once, to the finished dQ / dK accumulators.
 #pragma once
+#include <type_traits>
+
 #include "fa_simt.cuh"   // ld_as_float
 #include "ptx.cuh"
 
@@ -45,6 +47,17 @@
   } while (0)
 #else
 #define FA_BWD_TRACE_AT(role, step, slot) do { } while (0)
+#endif
+
+// Of every FA_BWD_POLY_DEN consecutive element pairs of P, the first FA_BWD_POLY_NUM get exp2 from the FMA-pipe polynomial
+// (ptx.cuh: exp2_poly2, relative error 7.5e-5 — P is rounded to 16 bits right after) instead of MUFU.EX2: both launches evaluate
+// every P element, 16384 per 128 x 128 step at 16 per clock, and the traces show the exp pass, not the tensor pipe, setting the
+// step time (profiles/r02_bwd_trace_v3_stream128.txt).
+#ifndef FA_BWD_POLY_NUM
+#define FA_BWD_POLY_NUM 1
+#endif
+#ifndef FA_BWD_POLY_DEN
+#define FA_BWD_POLY_DEN 2
 #endif
 
 namespace fa {
@@ -301,19 +314,35 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
       int c_lo = 0, c_hi = kBwdStr - 1;
       if (kDKV) {
         const int q0 = (i_first + step % per_head) * kBwdStr;
+        c_hi = p.n_q - 1 - q0;                                         // (rows beyond n_q: LSE2 = +inf, but the polynomial exp2 clamps)
         if (p.causal) c_lo = my_row - p.causal_offset - q0;            // q0 + c + offset >= key
         if (!row_valid) c_lo = kBwdStr;
       } else {
         const int k0 = step * kBwdStr;
         c_hi = p.n_k - 1 - k0;
         if (p.causal) c_hi = min(c_hi, my_row + p.causal_offset - k0);
+        if (l2r == INFINITY) c_hi = -1;                                // a row beyond n_q, or one that sees no key at all
       }
       c_lo -= hh * kBwdHalf;
       c_hi -= hh * kBwdHalf;
       const bool masked = c_lo > 0 || c_hi < kBwdHalf - 1;
       const uint32_t s_l2 = sStats + st * T::kStatsBytes + hh * kBwdHalf * 4;
       const uint32_t s_d = s_l2 + kBwdStr * 4;
-      if (kDKV) mbar_wait(bar_full + 8 * st, (step / T::kStages) & 1, TAG_B_FULL);   // the statistics of this stage
+      // the statistics of this stage's 64 columns go to registers before S is waited for (LSE2 now, D after the exps)
+      float stat[kBwdHalf];
+      auto load_stats = [&](uint32_t addr) {
+#pragma unroll
+        for (int c4 = 0; c4 < kBwdHalf / 4; ++c4) {
+          uint32_t a0, a1, a2, a3;
+          ld_shared_v4(addr + c4 * 16, a0, a1, a2, a3);
+          stat[c4 * 4] = __uint_as_float(a0); stat[c4 * 4 + 1] = __uint_as_float(a1);
+          stat[c4 * 4 + 2] = __uint_as_float(a2); stat[c4 * 4 + 3] = __uint_as_float(a3);
+        }
+      };
+      if (kDKV) {
+        mbar_wait(bar_full + 8 * st, (step / T::kStages) & 1, TAG_B_FULL);
+        load_stats(s_l2);
+      }
 
       // ---- P = exp2(S c - LSE2) ----
       mbar_wait(bar_s, par, TAG_B_S);
@@ -327,25 +356,29 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         tc_fence_before();
         mbar_arrive(bar_p);
       }
+      // two copies of the pass: the masked one (a diagonal or tail tile: two compares and two selects per element) only when some
+      // thread of the warp needs it
+      auto exp_pass = [&](auto with_mask) {
 #pragma unroll
-      for (int c4 = 0; c4 < kBwdHalf / 4; ++c4) {
-        float lq[4];
-        if (kDKV) {
-          uint32_t a0, a1, a2, a3;
-          ld_shared_v4(s_l2 + c4 * 16, a0, a1, a2, a3);
-          lq[0] = __uint_as_float(a0); lq[1] = __uint_as_float(a1); lq[2] = __uint_as_float(a2); lq[3] = __uint_as_float(a3);
-        } else {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) lq[u] = l2r;
+        for (int i = 0; i < kBwdHalf / 2; ++i) {
+          const float l0 = kDKV ? stat[2 * i] : l2r, l1 = kDKV ? stat[2 * i + 1] : l2r;
+          float2 e;
+          if ((i % FA_BWD_POLY_DEN) < FA_BWD_POLY_NUM) {
+            e = exp2_poly2(ffma2(make_float2(pr[2 * i], pr[2 * i + 1]), make_float2(p.scale_log2, p.scale_log2), make_float2(-l0, -l1)));
+          } else {
+            e.x = ex2(fmaf(pr[2 * i], p.scale_log2, -l0));
+            e.y = ex2(fmaf(pr[2 * i + 1], p.scale_log2, -l1));
+          }
+          if constexpr (decltype(with_mask)::value) {
+            if (2 * i < c_lo || 2 * i > c_hi) e.x = 0.f;
+            if (2 * i + 1 < c_lo || 2 * i + 1 > c_hi) e.y = 0.f;
+          }
+          pr[2 * i] = e.x;
+          pr[2 * i + 1] = e.y;
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = c4 * 4 + u;
-          float e = ex2(fmaf(pr[c], p.scale_log2, -lq[u]));
-          if (masked && (c < c_lo || c > c_hi)) e = 0.f;
-          pr[c] = e;
-        }
-      }
+      };
+      if (__any_sync(0xffffffffu, masked)) exp_pass(std::true_type{});
+      else exp_pass(std::false_type{});
       if (tracer) FA_BWD_TRACE_AT(hh, step, 1);
       if (kDKV) {
         // P^T (two 16-bit values per column) goes over the first 32 of the thread's OWN 64 columns of S, which it has in registers
@@ -358,6 +391,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         mbar_arrive(bar_p);
       }
       if (tracer) FA_BWD_TRACE_AT(hh, step, 2);
+      if (kDKV) load_stats(s_d);
 
       // ---- dS = P (dP - D) ----
       mbar_wait(bar_dp, par, TAG_B_DP);
@@ -371,18 +405,12 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         tc_wait_ld();
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
-          float dq[4];
-          if (kDKV) {
-            uint32_t d0, d1, d2, d3;
-            ld_shared_v4(s_d + (h2 * 8 + c4) * 16, d0, d1, d2, d3);
-            dq[0] = __uint_as_float(d0); dq[1] = __uint_as_float(d1); dq[2] = __uint_as_float(d2); dq[3] = __uint_as_float(d3);
-          } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) dq[u] = dr;
-          }
           float dv[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) dv[u] = pr[h2 * 32 + c4 * 4 + u] * (dp[c4 * 4 + u] - dq[u]);
+          for (int u = 0; u < 4; ++u) {
+            const int c = h2 * 32 + c4 * 4 + u;
+            dv[u] = pr[c] * (dp[c4 * 4 + u] - (kDKV ? stat[c] : dr));
+          }
           dk[h2 * 16 + c4 * 2] = pack_16x2<kF16>(dv[0], dv[1]);
           dk[h2 * 16 + c4 * 2 + 1] = pack_16x2<kF16>(dv[2], dv[3]);
         }
