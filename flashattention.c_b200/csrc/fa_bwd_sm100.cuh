@@ -90,11 +90,16 @@ struct BwdTraits {
   static constexpr int kDChunks = kHeadDim * 2 / 128;            // 128-byte column chunks per row
   static constexpr int kChunkBytes = 128 * 128;                  // one TMA box: 128 rows x 128 bytes
   static constexpr int kTileBytes = kDChunks * kChunkBytes;      // resident and streamed tiles alike
-  static constexpr int kStageBytes = 2 * kTileBytes;             // the streamed pair
-  static constexpr int kStages = kDChunks == 1 ? 4 : 2;
-  static constexpr int kStatsBytes = 2 * kBwdStr * 4;            // LSE2[128] | D[128] of a streamed (Q, dO) tile
-  static constexpr int kNumBarriers = 1 + 2 * kStages + 4 + 1;
-  static constexpr int kSmemBytes = 2 * kTileBytes + kStages * (kStageBytes + kStatsBytes) + kNumBarriers * 8 + 16 + 1024;
+  // The two streamed tensors have rings of their own: a tile of the first (Q in the dK/dV launch, K in the dQ launch) is read by
+  // the step's first contraction (S) and by its last (dK / dQ), and its successor-but-one is needed only one contraction after
+  // that — with two buffers its TMA load sat on the critical path (profiles/r02_bwd_trace_v4_poly.txt) — so it gets three; a tile
+  // of the second (dO / V) is done with much earlier and two are enough.  At d = 128 that is 64 + 96 + 64 KB: all of SMEM.
+  static constexpr int kRing1 = kDChunks == 1 ? 4 : 3;
+  static constexpr int kRing2 = kDChunks == 1 ? 3 : 2;
+  static constexpr int kStatBytes = kBwdStr * 4;                 // LSE2[128] (rides with ring 1) or D[128] (ring 2) of a (Q, dO) tile
+  static constexpr int kNumBarriers = 1 + 2 * kRing1 + 2 * kRing2 + 4 + 1;
+  // (the dynamic SMEM window is 1024-byte aligned — checked at kernel entry — so there is no alignment slack: there is no room for it)
+  static constexpr int kSmemBytes = (2 + kRing1 + kRing2) * kTileBytes + (kRing1 + kRing2) * kStatBytes + kNumBarriers * 8 + 16;
   static constexpr int kTmemS = 0, kTmemDP = 128;                // S and dP: 128 fp32 columns each (P / dS alias them)
   static constexpr int kTmemAcc = 256;                           // acc0 at 256, acc1 at 256 + kHeadDim
   static_assert(kTmemAcc + 2 * kHeadDim <= 512, "TMEM budget");
@@ -115,16 +120,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_constant__ CUtensorMap tm_r2,
                     const __grid_constant__ CUtensorMap tm_t1, const __grid_constant__ CUtensorMap tm_t2, const BwdParams p) {
   using T = BwdTraits<kHeadDim>;
-  extern __shared__ uint8_t bwd_smem_raw[];
-  const uint32_t smem0 = (smem_u32(bwd_smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t bwd_smem_raw[];
+  const uint32_t smem0 = smem_u32(bwd_smem_raw);
+  if ((smem0 & 1023u) != 0u) __trap();                             // the SWIZZLE_128B tiles need it (see BwdTraits::kSmemBytes)
   const uint32_t sR1 = smem0;                                      // kDKV: K_j    else: Q_i
   const uint32_t sR2 = sR1 + T::kTileBytes;                        // kDKV: V_j    else: dO_i
-  const uint32_t sStage = sR2 + T::kTileBytes;                     // [kStages][t1 | t2]   kDKV: (Q, dO)   else: (K, V)
-  const uint32_t sStats = sStage + T::kStages * T::kStageBytes;    // [kStages][LSE2[128] | D[128]]  (kDKV)
-  const uint32_t bar_res = sStats + T::kStages * T::kStatsBytes;
-  const uint32_t bar_full = bar_res + 8;                           // [kStages]
-  const uint32_t bar_empty = bar_full + 8 * T::kStages;            // [kStages]
-  const uint32_t bar_s = bar_empty + 8 * T::kStages;               // S of the step complete
+  const uint32_t sT1 = sR2 + T::kTileBytes;                        // [kRing1]  kDKV: Q    else: K
+  const uint32_t sT2 = sT1 + T::kRing1 * T::kTileBytes;            // [kRing2]  kDKV: dO   else: V
+  const uint32_t sL2 = sT2 + T::kRing2 * T::kTileBytes;            // [kRing1][128]  LSE2 of the Q tile (kDKV)
+  const uint32_t sD = sL2 + T::kRing1 * T::kStatBytes;             // [kRing2][128]  D of the dO tile (kDKV)
+  const uint32_t bar_res = sD + T::kRing2 * T::kStatBytes;
+  const uint32_t bar_full1 = bar_res + 8;                          // [kRing1]
+  const uint32_t bar_empty1 = bar_full1 + 8 * T::kRing1;           // [kRing1]
+  const uint32_t bar_full2 = bar_empty1 + 8 * T::kRing1;           // [kRing2]
+  const uint32_t bar_empty2 = bar_full2 + 8 * T::kRing2;           // [kRing2]
+  const uint32_t bar_s = bar_empty2 + 8 * T::kRing2;               // S of the step complete
   const uint32_t bar_dp = bar_s + 8;                               // dP of the step complete
   const uint32_t bar_p = bar_dp + 8;                               // kDKV: P written over S   else: S is in registers (its columns are free)
   const uint32_t bar_ds = bar_p + 8;                               // dS written over dP
@@ -156,9 +166,13 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
 
   if (warp == 9 && lane == 0) {
     mbar_init(bar_res, 1);
-    for (int i = 0; i < T::kStages; ++i) {
-      mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, 1);
+    for (int i = 0; i < T::kRing1; ++i) {
+      mbar_init(bar_full1 + 8 * i, 1);
+      mbar_init(bar_empty1 + 8 * i, 1);
+    }
+    for (int i = 0; i < T::kRing2; ++i) {
+      mbar_init(bar_full2 + 8 * i, 1);
+      mbar_init(bar_empty2 + 8 * i, 1);
     }
     mbar_init(bar_s, 1);
     mbar_init(bar_dp, 1);
@@ -193,9 +207,6 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         tma_load_4d(sR2 + c * T::kChunkBytes, &tm_r2, bar_res, c * 64, row0, head_r, batch);
       }
       for (int step = 0; step < n_steps; ++step) {
-        const int st = step % T::kStages;
-        if (step >= T::kStages) mbar_wait(bar_empty + 8 * st, ((step / T::kStages) - 1) & 1, TAG_B_EMPTY);
-        FA_BWD_TRACE_AT(3, step, 0);
         int head_t, srow;
         if (kDKV) {
           head_t = head_r * p.kv_group + step / per_head;
@@ -204,17 +215,26 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
           head_t = head_r / p.kv_group;
           srow = step * kBwdStr;
         }
-        const uint32_t dst = sStage + st * T::kStageBytes;
-        mbar_arrive_expect_tx(bar_full + 8 * st, T::kStageBytes + (kDKV ? T::kStatsBytes : 0));
+        const int64_t stat_off = (static_cast<int64_t>(batch) * p.heads + head_t) * p.n_q_pad + srow;
+        {
+          const int s1 = step % T::kRing1;
+          if (step >= T::kRing1) mbar_wait(bar_empty1 + 8 * s1, ((step / T::kRing1) - 1) & 1, TAG_B_EMPTY);
+          FA_BWD_TRACE_AT(3, step, 0);
+          mbar_arrive_expect_tx(bar_full1 + 8 * s1, T::kTileBytes + (kDKV ? T::kStatBytes : 0));
 #pragma unroll
-        for (int c = 0; c < T::kDChunks; ++c) {
-          tma_load_4d(dst + c * T::kChunkBytes, &tm_t1, bar_full + 8 * st, c * 64, srow, head_t, batch);
-          tma_load_4d(dst + T::kTileBytes + c * T::kChunkBytes, &tm_t2, bar_full + 8 * st, c * 64, srow, head_t, batch);
+          for (int c = 0; c < T::kDChunks; ++c)
+            tma_load_4d(sT1 + s1 * T::kTileBytes + c * T::kChunkBytes, &tm_t1, bar_full1 + 8 * s1, c * 64, srow, head_t, batch);
+          if (kDKV) bulk_load(sL2 + s1 * T::kStatBytes, p.l2 + stat_off, T::kStatBytes, bar_full1 + 8 * s1);
         }
-        if (kDKV) {
-          const int64_t off = (static_cast<int64_t>(batch) * p.heads + head_t) * p.n_q_pad + srow;
-          bulk_load(sStats + st * T::kStatsBytes, p.l2 + off, kBwdStr * 4, bar_full + 8 * st);
-          bulk_load(sStats + st * T::kStatsBytes + kBwdStr * 4, p.dsum + off, kBwdStr * 4, bar_full + 8 * st);
+        {
+          const int s2 = step % T::kRing2;
+          if (step >= T::kRing2) mbar_wait(bar_empty2 + 8 * s2, ((step / T::kRing2) - 1) & 1, TAG_B_EMPTY);
+          FA_BWD_TRACE_AT(3, step, 1);
+          mbar_arrive_expect_tx(bar_full2 + 8 * s2, T::kTileBytes + (kDKV ? T::kStatBytes : 0));
+#pragma unroll
+          for (int c = 0; c < T::kDChunks; ++c)
+            tma_load_4d(sT2 + s2 * T::kTileBytes + c * T::kChunkBytes, &tm_t2, bar_full2 + 8 * s2, c * 64, srow, head_t, batch);
+          if (kDKV) bulk_load(sD + s2 * T::kStatBytes, p.dsum + stat_off, T::kStatBytes, bar_full2 + 8 * s2);
         }
       }
     }
@@ -239,13 +259,18 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
       const uint64_t r2d = sdesc_at(hi_kmajor, sR2);
       const uint32_t tS = tmem_base + T::kTmemS, tDP = tmem_base + T::kTmemDP;
       const uint32_t acc0 = tmem_base + T::kTmemAcc, acc1 = acc0 + kHeadDim;
-      auto wait_full = [&](int step) {
-        mbar_wait(bar_full + 8 * (step % T::kStages), (step / T::kStages) & 1, TAG_B_FULL);
+      // SMEM address of the step's tile of streamed tensor `which` (0: ring 1, 1: ring 2)
+      auto tile_of = [&](int step, int which) {
+        return which == 0 ? sT1 + (step % T::kRing1) * T::kTileBytes : sT2 + (step % T::kRing2) * T::kTileBytes;
+      };
+      auto wait_full = [&](int step, int which) {
+        if (which == 0) mbar_wait(bar_full1 + 8 * (step % T::kRing1), (step / T::kRing1) & 1, TAG_B_FULL);
+        else mbar_wait(bar_full2 + 8 * (step % T::kRing2), (step / T::kRing2) & 1, TAG_B_FULL);
         tc_fence_after();
       };
-      // D[tmem d] = R (resident, K-major) x T^T (streamed tile `which` of the step's stage, K-major)
+      // D[tmem d] = R (resident, K-major) x T^T (the step's tile of streamed tensor `which`, K-major)
       auto issue_rt = [&](uint32_t d, uint64_t rd, int step, int which) {
-        const uint64_t td = sdesc_at(hi_kmajor, sStage + (step % T::kStages) * T::kStageBytes + which * T::kTileBytes);
+        const uint64_t td = sdesc_at(hi_kmajor, tile_of(step, which));
 #pragma unroll
         for (int kk = 0; kk < kKStepsD; ++kk) {
           const uint32_t off = ((kk >> 2) * T::kChunkBytes + (kk & 3) * 32) >> 4;
@@ -254,26 +279,31 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
       };
       // acc += A (TMEM: packed P or dS, streamed rows [64 h, 64 h + 64) in columns [64 h, 64 h + 32) of its region) x T (MN-major)
       auto issue_acc = [&](uint32_t acc, uint32_t a, int step, int which) {
-        const uint64_t tm = sdesc_at(hi_mnmajor, sStage + (step % T::kStages) * T::kStageBytes + which * T::kTileBytes);
+        const uint64_t tm = sdesc_at(hi_mnmajor, tile_of(step, which));
 #pragma unroll
         for (int ks = 0; ks < kKStepsR; ++ks)
           mma_ts<false>(acc, a + static_cast<uint32_t>((ks >> 2) * kBwdHalf + (ks & 3) * 8), tm + static_cast<uint32_t>(ks * 128), idesc_acc,
                         (step > 0 || ks > 0) ? 1u : 0u);
       };
-      wait_full(0);
+      wait_full(0, 0);
       issue_rt(tS, r1d, 0, 0);
       tc_commit(bar_s);
+      wait_full(0, 1);
       issue_rt(tDP, r2d, 0, 1);
       tc_commit(bar_dp);
+      if (!kDKV) tc_commit(bar_empty2);                    // dQ launch: V_0 is only read by dP(0)
       for (int step = 0; step < n_steps; ++step) {
         const uint32_t par = static_cast<uint32_t>(step & 1);
         FA_BWD_TRACE_AT(2, step, 0);
         mbar_wait(bar_p, par, TAG_B_P);
         tc_fence_after();
         FA_BWD_TRACE_AT(2, step, 1);
-        if (kDKV) issue_acc(acc0, tS, step, 1);            // dV += P^T dO
+        if (kDKV) {
+          issue_acc(acc0, tS, step, 1);                    // dV += P^T dO
+          tc_commit(bar_empty2 + 8 * (step % T::kRing2));  // dO_i has been read by dP(i) and dV(i)
+        }
         if (step + 1 < n_steps) {
-          wait_full(step + 1);
+          wait_full(step + 1, 0);
           issue_rt(tS, r1d, step + 1, 0);                  // S of the next step
           tc_commit(bar_s);
         }
@@ -282,10 +312,12 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         tc_fence_after();
         FA_BWD_TRACE_AT(2, step, 3);
         issue_acc(kDKV ? acc1 : acc0, tDP, step, 0);       // dK += dS^T Q   /   dQ += dS K
-        tc_commit(bar_empty + 8 * (step % T::kStages));    // the stage's tiles have been read once everything issued so far completes
+        tc_commit(bar_empty1 + 8 * (step % T::kRing1));    // Q_i / K_j has been read by S and by dK / dQ once everything issued so far completes
         if (step + 1 < n_steps) {
+          wait_full(step + 1, 1);
           issue_rt(tDP, r2d, step + 1, 1);                 // dP of the next step
           tc_commit(bar_dp);
+          if (!kDKV) tc_commit(bar_empty2 + 8 * ((step + 1) % T::kRing2));   // dQ launch: V_j is only read by dP(j)
         }
         FA_BWD_TRACE_AT(2, step, 4);
       }
@@ -308,7 +340,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
     const uint32_t tDP = tmem_base + lane_base + T::kTmemDP + hh * kBwdHalf;   // ... and of dP
     const bool tracer = FA_BWD_TRACE && (warp & 3) == 0 && lane == 0;
     for (int step = 0; step < n_steps; ++step) {
-      const int st = step % T::kStages;
+      const int s1 = step % T::kRing1, s2 = step % T::kRing2;
       const uint32_t par = static_cast<uint32_t>(step & 1);
       // column c (0 .. 127) of this step is visible to this thread's row iff c_lo <= c <= c_hi; then in its own numbering (0 .. 63)
       int c_lo = 0, c_hi = kBwdStr - 1;
@@ -326,8 +358,8 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
       c_lo -= hh * kBwdHalf;
       c_hi -= hh * kBwdHalf;
       const bool masked = c_lo > 0 || c_hi < kBwdHalf - 1;
-      const uint32_t s_l2 = sStats + st * T::kStatsBytes + hh * kBwdHalf * 4;
-      const uint32_t s_d = s_l2 + kBwdStr * 4;
+      const uint32_t s_l2 = sL2 + s1 * T::kStatBytes + hh * kBwdHalf * 4;
+      const uint32_t s_d = sD + s2 * T::kStatBytes + hh * kBwdHalf * 4;
       // the statistics of this stage's 64 columns go to registers before S is waited for (LSE2 now, D after the exps)
       float stat[kBwdHalf];
       auto load_stats = [&](uint32_t addr) {
@@ -340,7 +372,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         }
       };
       if (kDKV) {
-        mbar_wait(bar_full + 8 * st, (step / T::kStages) & 1, TAG_B_FULL);
+        mbar_wait(bar_full1 + 8 * s1, (step / T::kRing1) & 1, TAG_B_FULL);
         load_stats(s_l2);
       }
 
@@ -391,7 +423,10 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         mbar_arrive(bar_p);
       }
       if (tracer) FA_BWD_TRACE_AT(hh, step, 2);
-      if (kDKV) load_stats(s_d);
+      if (kDKV) {
+        mbar_wait(bar_full2 + 8 * s2, (step / T::kRing2) & 1, TAG_B_FULL);
+        load_stats(s_d);
+      }
 
       // ---- dS = P (dP - D) ----
       mbar_wait(bar_dp, par, TAG_B_DP);
