@@ -432,6 +432,32 @@ def other_configs(torch, fab, device, flush, peaks):
                                                  "frac_hbm_peak": round(kv_bytes / ms * 1e-6 / peaks["hbm"], 4),
                                                  "note": "split-KV across CTAs + fa_combine_splits_kernel (2 launches); bytes = K + V read once"}
     del q, k, v, out
+    # the backward pass (not in the reference, which is forward only) on the C4 shape: statistics + dK/dV + dQ launches.
+    # FLOPs: algorithmic = 2.5 x forward (five contractions); executed = 3.5 x (the dQ launch recomputes S and dP instead of reducing
+    # dQ across CTAs with atomics).  torch's scaled_dot_product_attention flash backward on the same tensors is timed beside it as a
+    # library yardstick (a library kernel, not the reference).
+    B, H, N, d, _ = WORKLOADS["C4"]
+    for label, causal in (("C4_backward_bf16", False), ("C4_backward_bf16_causal", True)):
+        g = torch.Generator(device=device).manual_seed(11)
+        q, k, v, do = (torch.randn(B, H, N, d, device=device, generator=g).to(torch.bfloat16) for _ in range(4))
+        scale = 1.0 / math.sqrt(d)
+        o, lse = fab.attention(q, k, v, causal=causal, scale=scale, return_lse=True)
+        ms = sorted(time_kernel(torch, lambda: fab.attention_backward(q, k, v, o, lse, do, causal=causal, scale=scale), 6, 2, flush))[3]
+        alg = 2.5 * flops_of(B, H, N, d) * (0.5 if causal else 1.0)
+        row = {"ms": round(ms, 4), "tflops_algorithmic_5_contractions": round(alg / ms * 1e-9, 1),
+               "tflops_executed_7_contractions": round(1.4 * alg / ms * 1e-9, 1),
+               "frac_tensor_peak_executed": round(1.4 * alg / ms * 1e-9 / peaks["bf16"], 4), "launches": 3}
+        try:
+            qq, kk, vv = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+            with torch.nn.attention.sdpa_kernel(torch.nn.attention.SDPBackend.FLASH_ATTENTION):
+                oo = torch.nn.functional.scaled_dot_product_attention(qq, kk, vv, is_causal=causal, scale=scale)
+                row["torch_sdpa_flash_backward_ms"] = round(sorted(time_kernel(torch, lambda: oo.backward(do, retain_graph=True), 4, 1, flush))[2], 4)
+            del qq, kk, vv, oo
+        except Exception as ex:  # noqa: BLE001  (a yardstick only: its absence is reported, not fatal)
+            row["torch_sdpa_flash_backward_ms"] = None
+            row["torch_sdpa_note"] = repr(ex)[:100]
+        res[label] = row
+        del q, k, v, do, o, lse
     # config 5 on ONE GPU: the whole 131072-long sequence in one launch (the ring's single-GPU baseline)
     Hh, Nn, dd = 32, 131072, 128
     g = torch.Generator(device=device).manual_seed(5)

@@ -316,26 +316,29 @@ int run_bwd(const fa_bwd_params* p, cudaStream_t st) {
   } ws_free{ws_async, st};
   float* l2 = static_cast<float*>(ws);
   float* dsum = l2 + rows_pad;
-  {
-    const int64_t blocks = (rows_pad + 7) / 8;
-    if (blocks > 0x7fffffff) return FA_ERR_INVALID_ARG;
-    if (f16)
-      fa::fa_bwd_prep_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(
-          static_cast<const __half*>(p->o), p->o_stride_b, p->o_stride_h, p->o_stride_n, static_cast<const __half*>(p->d_o), p->do_stride_b,
-          p->do_stride_h, p->do_stride_n, p->lse, l2, dsum, (int)p->heads, (int)p->n_q, (int)n_q_pad, p->head_dim, rows_pad);
-    else
-      fa::fa_bwd_prep_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(
-          static_cast<const __nv_bfloat16*>(p->o), p->o_stride_b, p->o_stride_h, p->o_stride_n, static_cast<const __nv_bfloat16*>(p->d_o),
-          p->do_stride_b, p->do_stride_h, p->do_stride_n, p->lse, l2, dsum, (int)p->heads, (int)p->n_q, (int)n_q_pad, p->head_dim, rows_pad);
-    FA_CUDA(cudaGetLastError());
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-  }
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
   CUtensorMap mq, mg, mk, mv;   // one box shape (128 rows x 128 bytes) serves the resident and the streamed role of each tensor
   if ((rc = make_map(&mq, p->q, 2, dt, p->batch, p->heads, p->n_q, p->head_dim, p->q_stride_b, p->q_stride_h, p->q_stride_n, sw))) return rc;
   if ((rc = make_map(&mg, p->d_o, 2, dt, p->batch, p->heads, p->n_q, p->head_dim, p->do_stride_b, p->do_stride_h, p->do_stride_n, sw))) return rc;
   if ((rc = make_map(&mk, p->k, 2, dt, p->batch, kv_heads, p->n_k, p->head_dim, p->k_stride_b, p->k_stride_h, p->k_stride_n, sw))) return rc;
   if ((rc = make_map(&mv, p->v, 2, dt, p->batch, kv_heads, p->n_k, p->head_dim, p->v_stride_b, p->v_stride_h, p->v_stride_n, sw))) return rc;
+  // statistics pass (after the tensor maps: building them checks the alignment of every operand, dO included)
+  {
+    int tpr = 1;                                       // threads per row: 16-byte pieces, rounded up to a power of two
+    while (tpr * 8 < p->head_dim) tpr *= 2;
+    const int64_t blocks = (rows_pad * tpr + 255) / 256;
+    if (blocks > 0x7fffffff) return FA_ERR_INVALID_ARG;
+    if (f16)
+      fa::fa_bwd_prep_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(
+          static_cast<const __half*>(p->o), p->o_stride_b, p->o_stride_h, p->o_stride_n, static_cast<const __half*>(p->d_o), p->do_stride_b,
+          p->do_stride_h, p->do_stride_n, p->lse, l2, dsum, (int)p->heads, (int)p->n_q, (int)n_q_pad, p->head_dim, tpr, rows_pad);
+    else
+      fa::fa_bwd_prep_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(p->o), p->o_stride_b, p->o_stride_h, p->o_stride_n, static_cast<const __nv_bfloat16*>(p->d_o),
+          p->do_stride_b, p->do_stride_h, p->do_stride_n, p->lse, l2, dsum, (int)p->heads, (int)p->n_q, (int)n_q_pad, p->head_dim, tpr, rows_pad);
+    FA_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   fa::BwdParams bp;
   memset(&bp, 0, sizeof(bp));
   bp.scale = p->scale;
@@ -731,7 +734,8 @@ int fa_backward(const fa_bwd_params* p, void* stream) {
   if (p->kv_heads < 0 || (p->kv_heads > 0 && (p->kv_heads > p->heads || p->heads % p->kv_heads != 0))) return FA_ERR_INVALID_ARG;
   if (p->dtype != FA_BF16 && p->dtype != FA_F16) return p->dtype == FA_F32 ? FA_ERR_UNSUPPORTED : FA_ERR_INVALID_ARG;
   if (p->head_dim % 8 != 0 || p->head_dim > 128) return FA_ERR_UNSUPPORTED;
-  // the epilogue writes 16-byte vectors; O is read element-wise
+  // the epilogue writes 16-byte vectors and the statistics pass reads O with them (dO is checked with its tensor map)
+  if ((reinterpret_cast<uintptr_t>(p->o) & 15) || p->o_stride_b % 8 || p->o_stride_h % 8 || p->o_stride_n % 8) return FA_ERR_ALIGNMENT;
   const void* outs[3] = {p->dq, p->dk, p->dv};
   const int64_t ostr[9] = {p->dq_stride_b, p->dq_stride_h, p->dq_stride_n, p->dk_stride_b, p->dk_stride_h, p->dk_stride_n,
                            p->dv_stride_b, p->dv_stride_h, p->dv_stride_n};

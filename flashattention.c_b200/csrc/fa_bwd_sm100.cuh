@@ -511,29 +511,36 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
   }
 }
 
-// D[row] = sum_c dO[row, c] * O[row, c] and LSE2[row] = LSE[row] * log2(e) into the padded workspace; one warp per padded row.
+// D[row] = sum_c dO[row, c] * O[row, c] and LSE2[row] = LSE[row] * log2(e) into the padded workspace.  A row is read by `tpr`
+// neighbouring threads (a power of two >= head_dim / 8), 16 bytes each, so a warp's loads cover whole contiguous rows.
 template <typename T16>
 __global__ void __launch_bounds__(256)
 fa_bwd_prep_kernel(const T16* __restrict__ o, int64_t o_sb, int64_t o_sh, int64_t o_sn, const T16* __restrict__ d_o, int64_t g_sb,
                    int64_t g_sh, int64_t g_sn, const float* __restrict__ lse, float* __restrict__ l2, float* __restrict__ dsum,
-                   int heads, int n_q, int n_q_pad, int d, int64_t rows_pad) {
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (idx >= rows_pad) return;
-  const int64_t bh = idx / n_q_pad;
-  const int row = static_cast<int>(idx % n_q_pad);
-  float acc = 0.f, l = INFINITY;
-  if (row < n_q) {
+                   int heads, int n_q, int n_q_pad, int d, int tpr, int64_t rows_pad) {
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t idx = tid / tpr;          // padded row
+  const int piece = static_cast<int>(tid % tpr);
+  const bool live = idx < rows_pad;       // (the shuffles below need every lane of the warp)
+  const int64_t bh = live ? idx / n_q_pad : 0;
+  const int row = live ? static_cast<int>(idx % n_q_pad) : n_q;
+  float acc = 0.f;
+  if (row < n_q && piece * 8 < d) {
     const int64_t b = bh / heads, h = bh % heads;
-    const T16* po = o + b * o_sb + h * o_sh + static_cast<int64_t>(row) * o_sn;
-    const T16* pg = d_o + b * g_sb + h * g_sh + static_cast<int64_t>(row) * g_sn;
-    for (int c = lane; c < d; c += 32) acc = fmaf(ld_as_float(po + c), ld_as_float(pg + c), acc);
+    const uint4 vo = *reinterpret_cast<const uint4*>(o + b * o_sb + h * o_sh + static_cast<int64_t>(row) * o_sn + piece * 8);
+    const uint4 vg = *reinterpret_cast<const uint4*>(d_o + b * g_sb + h * g_sh + static_cast<int64_t>(row) * g_sn + piece * 8);
+    const T16* po = reinterpret_cast<const T16*>(&vo);
+    const T16* pg = reinterpret_cast<const T16*>(&vg);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    const float x = lse[bh * n_q + row];
-    l = (x == -INFINITY) ? INFINITY : x * 1.4426950408889634f;
+    for (int i = 0; i < 8; ++i) acc = fmaf(ld_as_float(po + i), ld_as_float(pg + i), acc);
   }
-  if (lane == 0) {
+  for (int off = tpr >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (live && piece == 0) {
+    float l = INFINITY;
+    if (row < n_q) {
+      const float x = lse[bh * n_q + row];
+      l = (x == -INFINITY) ? INFINITY : x * 1.4426950408889634f;
+    }
     l2[idx] = l;
     dsum[idx] = acc;
   }
