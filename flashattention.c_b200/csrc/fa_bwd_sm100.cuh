@@ -440,14 +440,13 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         tc_wait_ld();
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
-          float dv[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = h2 * 32 + c4 * 4 + u;
-            dv[u] = pr[c] * (dp[c4 * 4 + u] - (kDKV ? stat[c] : dr));
+          for (int u = 0; u < 2; ++u) {   // packed FADD2 / FMUL2: one instruction per two elements
+            const int c = h2 * 32 + c4 * 4 + 2 * u;
+            const float2 nd = kDKV ? make_float2(-stat[c], -stat[c + 1]) : make_float2(-dr, -dr);
+            const float2 dv = fmul2(make_float2(pr[c], pr[c + 1]), fadd2(make_float2(dp[c4 * 4 + 2 * u], dp[c4 * 4 + 2 * u + 1]), nd));
+            dk[h2 * 16 + c4 * 2 + u] = pack_16x2<kF16>(dv.x, dv.y);
           }
-          dk[h2 * 16 + c4 * 2] = pack_16x2<kF16>(dv[0], dv[1]);
-          dk[h2 * 16 + c4 * 2 + 1] = pack_16x2<kF16>(dv[2], dv[3]);
         }
       }
       // dS over the first 32 of the thread's own 64 columns of dP (all 64 are in registers by now)

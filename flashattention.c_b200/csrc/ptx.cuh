@@ -278,6 +278,15 @@ FA_DEVINL float2 fadd2(float2 a, float2 b) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
   return d;
 }
+FA_DEVINL float2 fmul2(float2 a, float2 b) {
+  uint64_t ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
 // exp2 on the FMA/ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax
 // polynomial (max relative error 7.5e-5, well under the bf16 / tf32 quantisation of P), 2^n by adding n to the
 // exponent field.  The magic constant 1.5 * 2^23 leaves round(x) in the low mantissa bits of (x + magic).

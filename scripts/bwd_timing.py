@@ -2,6 +2,7 @@
 FLOPs: algorithmic = 10 B H N_q N_k d (five contractions: the single-pass count; causal halves it); executed = 14 B H N_q N_k d
 (seven: S and dP are recomputed by the dQ launch)."""
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -48,6 +49,8 @@ def main():
                 "bwd_tflops_algorithmic_5gemm": round(alg / mb / 1e9, 1), "bwd_tflops_executed_7gemm": round(1.4 * alg / mb / 1e9, 1)}
         # library baseline beside it: torch SDPA (flash backend) backward on the same tensors
         try:
+            if os.environ.get("BWD_NO_TORCH"):
+                raise RuntimeError("skipped (BWD_NO_TORCH)")
             qq, kk, vv = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
             with torch.nn.attention.sdpa_kernel(torch.nn.attention.SDPBackend.FLASH_ATTENTION):
                 oo = torch.nn.functional.scaled_dot_product_attention(qq, kk, vv, is_causal=causal, scale=scale)

@@ -196,3 +196,31 @@ def test_backward_randomised_shapes(fab, cuda_device, seed):
             worst = max(worst, e / TOL[dtype])
             assert e < TOL[dtype], (case, name, (B, H, Hk, nq, nk, d, dtype, causal, scale), e)
     print(f"worst error / tolerance over 40 cases: {worst:.3f}")
+
+
+def test_forward_and_backward_under_cuda_graph_capture(fab, cuda_device):
+    """A training step's attention — forward with LSE, then the three backward launches — captured once and replayed on new data.
+    Under capture the backward's statistics workspace is a stream-ordered allocation of the graph (cudaMallocAsync / cudaFreeAsync
+    nodes) instead of the per-stream cached buffer."""
+    g0 = torch.Generator().manual_seed(21)
+    q, k, v, do = (torch.randn(2, 4, 600, 64, generator=g0).to(torch.bfloat16).to(cuda_device) for _ in range(4))
+    o, lse = fab.attention(q, k, v, causal=True, return_lse=True)                 # warm-up outside capture
+    fab.attention_backward(q, k, v, o, lse, do, causal=True)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(graph, stream=s):
+            o_c, lse_c = fab.attention(q, k, v, causal=True, return_lse=True)
+            grads_c = fab.attention_backward(q, k, v, o_c, lse_c, do, causal=True)
+    torch.cuda.current_stream().wait_stream(s)
+    for t in (q, k, v, do):                                                       # new data in the captured buffers
+        t.copy_(torch.randn(t.shape, generator=g0).to(torch.bfloat16))
+    graph.replay()
+    torch.cuda.synchronize()
+    o_e, lse_e = fab.attention(q, k, v, causal=True, return_lse=True)
+    grads_e = fab.attention_backward(q, k, v, o_e, lse_e, do, causal=True)
+    torch.cuda.synchronize()
+    assert torch.equal(o_c, o_e)
+    for a, b in zip(grads_c, grads_e):
+        assert torch.equal(a, b)
