@@ -394,12 +394,12 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
 #pragma unroll
         for (int i = 0; i < kBwdHalf / 2; ++i) {
           const float l0 = kDKV ? stat[2 * i] : l2r, l1 = kDKV ? stat[2 * i + 1] : l2r;
-          float2 e;
+          float2 e = ffma2(make_float2(pr[2 * i], pr[2 * i + 1]), make_float2(p.scale_log2, p.scale_log2), make_float2(-l0, -l1));
           if ((i % FA_BWD_POLY_DEN) < FA_BWD_POLY_NUM) {
-            e = exp2_poly2(ffma2(make_float2(pr[2 * i], pr[2 * i + 1]), make_float2(p.scale_log2, p.scale_log2), make_float2(-l0, -l1)));
+            e = exp2_poly2(e);
           } else {
-            e.x = ex2(fmaf(pr[2 * i], p.scale_log2, -l0));
-            e.y = ex2(fmaf(pr[2 * i + 1], p.scale_log2, -l1));
+            e.x = ex2(e.x);
+            e.y = ex2(e.y);
           }
           if constexpr (decltype(with_mask)::value) {
             if (2 * i < c_lo || 2 * i > c_hi) e.x = 0.f;
