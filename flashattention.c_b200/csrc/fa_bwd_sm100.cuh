@@ -5,7 +5,7 @@
 // Two launches of ONE kernel template, both atomics-free and deterministic:
 //   kDKV = true   a CTA owns 128 keys of one K/V head (resident tiles K_j, V_j) and streams 128-row tiles of (Q, dO) of every
 //                 query head of its group:   S^T = K Q^T,  dP^T = V dO^T   (tcgen05.mma, A and B from SMEM, D in TMEM)
-//                 P^T = exp2(S^T c - LSE2[q]),  dS^T = P^T (dP^T - D[q])   (one thread per key row, statistics per column)
+//                 P^T = exp2(S^T c - LSE2[q]),  dS^T = P^T (dP^T - D[q])   (two threads per key row, statistics per column)
 //                 dV += P^T dO,  dK += dS^T Q                              (A = P^T / dS^T read straight from TMEM)
 //   kDKV = false  a CTA owns 128 query rows of one head (resident Q_i, dO_i) and streams 128-key tiles of (K, V):
 //                 S = Q K^T,  dP = dO V^T,  dS = P (dP - D[q])  (statistics per row, in registers),  dQ += dS K
@@ -18,7 +18,7 @@
 // D[q] = rowsum(dO * O) and LSE2[q] = LSE * log2(e) come from fa_bwd_prep_kernel in a workspace whose rows are padded to a
 // multiple of 128 per (batch, head) (+inf / 0 in the padding and for rows that saw no key: P = exp2(x - inf) = 0 there).
 //
-// Pipeline: warp 8 lane 0 = TMA producer (ring of streamed tile pairs), warp 9 lane 0 = MMA issuer, warps 0-7 = two threads per
+// Pipeline: warp 8 lane 0 = TMA producer (one ring per streamed tensor), warp 9 lane 0 = MMA issuer, warps 0-7 = two threads per
 // TMEM lane (warp w: lanes 32 (w % 4) .. + 31, columns 64 (w / 4) .. + 63 of S and dP).  Streamed tiles are 128 rows: every
 // contraction is then a run of eight 128 x 128 x 16 MMAs at the full tensor rate (64-row tiles were measured first: their
 // 128 x 64 MMAs cost 54 instead of 33.5 cycles per 64 columns, and the fixed costs per step — barrier waits, the switch between
