@@ -79,10 +79,18 @@ struct BwdParams {
   unsigned long long* trace;   // FA_BWD_TRACE builds only; nullptr otherwise
 };
 
-constexpr int kBwdThreads = 320;   // 8 compute warps + producer warp + MMA warp
+// threads per TMEM lane in the element-wise pass (2: 8 warps, 64 columns of S / dP per thread; 4: 16 warps, 32 columns)
+#ifndef FA_BWD_SPLIT
+#define FA_BWD_SPLIT 2
+#endif
+constexpr int kBwdSplit = FA_BWD_SPLIT;
+static_assert(kBwdSplit == 2 || kBwdSplit == 4, "two or four threads per TMEM lane");
+constexpr int kBwdThreads = (4 * kBwdSplit + 2) * 32;   // compute warps + producer warp + MMA warp
+constexpr int kBwdProdWarp = 4 * kBwdSplit, kBwdMmaWarp = 4 * kBwdSplit + 1;
+constexpr bool kBwdStatRegs = kBwdSplit == 2;            // per-column statistics held in registers (else read from SMEM where used)
 constexpr int kBwdRes = 128;       // rows of a resident tile (keys of the dK/dV launch, query rows of the dQ launch)
 constexpr int kBwdStr = 128;       // rows of a streamed tile
-constexpr int kBwdHalf = 64;       // S / dP columns per compute thread (two threads share a TMEM lane)
+constexpr int kBwdHalf = 128 / kBwdSplit;   // S / dP columns per compute thread
 
 template <int kHeadDim>
 struct BwdTraits {
@@ -164,7 +172,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
     n_steps = last < 0 ? 0 : last / kBwdStr + 1;
   }
 
-  if (warp == 9 && lane == 0) {
+  if (warp == kBwdMmaWarp && lane == 0) {
     mbar_init(bar_res, 1);
     for (int i = 0; i < T::kRing1; ++i) {
       mbar_init(bar_full1 + 8 * i, 1);
@@ -176,12 +184,12 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
     }
     mbar_init(bar_s, 1);
     mbar_init(bar_dp, 1);
-    mbar_init(bar_p, 256);
-    mbar_init(bar_ds, 256);
+    mbar_init(bar_p, 128 * kBwdSplit);
+    mbar_init(bar_ds, 128 * kBwdSplit);
     mbar_init(bar_acc, 1);
     fence_mbar_init();
   }
-  if (warp == 8) {
+  if (warp == kBwdProdWarp) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_r1);
       tma_prefetch_desc(&tm_r2);
@@ -197,7 +205,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(s_tmem_ptr));
 
-  if (warp == 8) {
+  if (warp == kBwdProdWarp) {
     // =========================== TMA producer ===========================
     if (lane == 0 && n_steps > 0) {
       mbar_arrive_expect_tx(bar_res, 2 * T::kTileBytes);
@@ -238,7 +246,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kBwdMmaWarp) {
     // =========================== MMA issuer ===========================
     // Order on the (in-order) tensor pipe:  S(0) dP(0) | then per step i:  [P(i)] dV(i)  S(i+1)  [dS(i)] dK(i)  dP(i+1)
     // (dQ launch: no dV; dK -> dQ).  S(i+1) overwrites the S columns once dV(i) has read P(i) out of them, dP(i+1) the dP columns
@@ -277,12 +285,14 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
           mma_ss<false>(d, rd + off, td + off, idesc_sd, kk > 0 ? 1u : 0u);
         }
       };
-      // acc += A (TMEM: packed P or dS, streamed rows [64 h, 64 h + 64) in columns [64 h, 64 h + 32) of its region) x T (MN-major)
+      // acc += A (TMEM: packed P or dS; the streamed rows [kBwdHalf h, kBwdHalf (h + 1)) of thread group h sit in the first half of
+      // that group's own columns of the region) x T (MN-major)
       auto issue_acc = [&](uint32_t acc, uint32_t a, int step, int which) {
         const uint64_t tm = sdesc_at(hi_mnmajor, tile_of(step, which));
 #pragma unroll
         for (int ks = 0; ks < kKStepsR; ++ks)
-          mma_ts<false>(acc, a + static_cast<uint32_t>((ks >> 2) * kBwdHalf + (ks & 3) * 8), tm + static_cast<uint32_t>(ks * 128), idesc_acc,
+          mma_ts<false>(acc, a + static_cast<uint32_t>((ks / (kBwdHalf / 16)) * kBwdHalf + (ks % (kBwdHalf / 16)) * 8),
+                        tm + static_cast<uint32_t>(ks * 128), idesc_acc,
                         (step > 0 || ks > 0) ? 1u : 0u);
       };
       wait_full(0, 0);
@@ -338,7 +348,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
     const bool row_valid = kDKV ? (my_row < p.n_k) : true;   // (query rows beyond n_q have LSE2 = +inf)
     const uint32_t tS = tmem_base + lane_base + T::kTmemS + hh * kBwdHalf;     // this thread's 64 columns of S ...
     const uint32_t tDP = tmem_base + lane_base + T::kTmemDP + hh * kBwdHalf;   // ... and of dP
-    const bool tracer = FA_BWD_TRACE && (warp & 3) == 0 && lane == 0;
+    const bool tracer = FA_BWD_TRACE && (warp & 3) == 0 && lane == 0 && hh < 2;
     for (int step = 0; step < n_steps; ++step) {
       const int s1 = step % T::kRing1, s2 = step % T::kRing2;
       const uint32_t par = static_cast<uint32_t>(step & 1);
@@ -360,15 +370,29 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
       const bool masked = c_lo > 0 || c_hi < kBwdHalf - 1;
       const uint32_t s_l2 = sL2 + s1 * T::kStatBytes + hh * kBwdHalf * 4;
       const uint32_t s_d = sD + s2 * T::kStatBytes + hh * kBwdHalf * 4;
-      // the statistics of this stage's 64 columns go to registers before S is waited for (LSE2 now, D after the exps)
-      float stat[kBwdHalf];
+      // the statistics of this thread's columns: in registers, loaded before S is waited for (LSE2 now, D after the exps), or —
+      // with four threads per lane, where the register file has no room for them — read from SMEM where they are used
+      float stat[kBwdStatRegs ? kBwdHalf : 4];
       auto load_stats = [&](uint32_t addr) {
+        if constexpr (kBwdStatRegs) {
 #pragma unroll
-        for (int c4 = 0; c4 < kBwdHalf / 4; ++c4) {
+          for (int c4 = 0; c4 < kBwdHalf / 4; ++c4) {
+            uint32_t a0, a1, a2, a3;
+            ld_shared_v4(addr + c4 * 16, a0, a1, a2, a3);
+            stat[c4 * 4] = __uint_as_float(a0); stat[c4 * 4 + 1] = __uint_as_float(a1);
+            stat[c4 * 4 + 2] = __uint_as_float(a2); stat[c4 * 4 + 3] = __uint_as_float(a3);
+          }
+        }
+      };
+      // statistics of columns 4 c4 .. 4 c4 + 3
+      auto stat_quad = [&](uint32_t addr, int c4, float (&out)[4]) {
+        if constexpr (kBwdStatRegs) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) out[u] = stat[c4 * 4 + u];
+        } else {
           uint32_t a0, a1, a2, a3;
           ld_shared_v4(addr + c4 * 16, a0, a1, a2, a3);
-          stat[c4 * 4] = __uint_as_float(a0); stat[c4 * 4 + 1] = __uint_as_float(a1);
-          stat[c4 * 4 + 2] = __uint_as_float(a2); stat[c4 * 4 + 3] = __uint_as_float(a3);
+          out[0] = __uint_as_float(a0); out[1] = __uint_as_float(a1); out[2] = __uint_as_float(a2); out[3] = __uint_as_float(a3);
         }
       };
       if (kDKV) {
@@ -381,8 +405,8 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
       tc_fence_after();
       if (tracer) FA_BWD_TRACE_AT(hh, step, 0);
       float pr[kBwdHalf];
-      tmem_ld32(tS, reinterpret_cast<uint32_t*>(&pr[0]));
-      tmem_ld32(tS + 32, reinterpret_cast<uint32_t*>(&pr[32]));
+#pragma unroll
+      for (int q = 0; q < kBwdHalf / 32; ++q) tmem_ld32(tS + q * 32, reinterpret_cast<uint32_t*>(&pr[q * 32]));
       tc_wait_ld();
       if (!kDKV) {   // S is in registers and nothing is written back over it: the next S may be issued
         tc_fence_before();
@@ -392,32 +416,38 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
       // thread of the warp needs it
       auto exp_pass = [&](auto with_mask) {
 #pragma unroll
-        for (int i = 0; i < kBwdHalf / 2; ++i) {
-          const float l0 = kDKV ? stat[2 * i] : l2r, l1 = kDKV ? stat[2 * i + 1] : l2r;
-          float2 e = ffma2(make_float2(pr[2 * i], pr[2 * i + 1]), make_float2(p.scale_log2, p.scale_log2), make_float2(-l0, -l1));
-          if ((i % FA_BWD_POLY_DEN) < FA_BWD_POLY_NUM) {
-            e = exp2_poly2(e);
-          } else {
-            e.x = ex2(e.x);
-            e.y = ex2(e.y);
+        for (int c4 = 0; c4 < kBwdHalf / 4; ++c4) {
+          float lq[4] = {l2r, l2r, l2r, l2r};
+          if (kDKV) stat_quad(s_l2, c4, lq);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = c4 * 2 + u;   // pair index: columns 2 i, 2 i + 1
+            float2 e = ffma2(make_float2(pr[2 * i], pr[2 * i + 1]), make_float2(p.scale_log2, p.scale_log2), make_float2(-lq[2 * u], -lq[2 * u + 1]));
+            if ((i % FA_BWD_POLY_DEN) < FA_BWD_POLY_NUM) {
+              e = exp2_poly2(e);
+            } else {
+              e.x = ex2(e.x);
+              e.y = ex2(e.y);
+            }
+            if constexpr (decltype(with_mask)::value) {
+              if (2 * i < c_lo || 2 * i > c_hi) e.x = 0.f;
+              if (2 * i + 1 < c_lo || 2 * i + 1 > c_hi) e.y = 0.f;
+            }
+            pr[2 * i] = e.x;
+            pr[2 * i + 1] = e.y;
           }
-          if constexpr (decltype(with_mask)::value) {
-            if (2 * i < c_lo || 2 * i > c_hi) e.x = 0.f;
-            if (2 * i + 1 < c_lo || 2 * i + 1 > c_hi) e.y = 0.f;
-          }
-          pr[2 * i] = e.x;
-          pr[2 * i + 1] = e.y;
         }
       };
       if (__any_sync(0xffffffffu, masked)) exp_pass(std::true_type{});
       else exp_pass(std::false_type{});
       if (tracer) FA_BWD_TRACE_AT(hh, step, 1);
       if (kDKV) {
-        // P^T (two 16-bit values per column) goes over the first 32 of the thread's OWN 64 columns of S, which it has in registers
+        // P^T (two 16-bit values per column) goes over the first half of the thread's OWN columns of S, which it has in registers
         uint32_t pk[kBwdHalf / 2];
 #pragma unroll
         for (int i = 0; i < kBwdHalf / 2; ++i) pk[i] = pack_16x2<kF16>(pr[2 * i], pr[2 * i + 1]);
-        tmem_st32(tS, pk);
+        if constexpr (kBwdHalf == 64) tmem_st32(tS, pk);
+        else tmem_st16(tS, pk);
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(bar_p);
@@ -434,23 +464,26 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
       if (tracer) FA_BWD_TRACE_AT(hh, step, 3);
       uint32_t dk[kBwdHalf / 2];
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {   // in two pieces of 32 columns: 32 live dP registers instead of 64
+      for (int h2 = 0; h2 < kBwdHalf / 32; ++h2) {   // in pieces of 32 columns: 32 live dP registers
         float dp[32];
         tmem_ld32(tDP + h2 * 32, reinterpret_cast<uint32_t*>(&dp[0]));
         tc_wait_ld();
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
+          float dq[4] = {dr, dr, dr, dr};
+          if (kDKV) stat_quad(s_d, h2 * 8 + c4, dq);
 #pragma unroll
           for (int u = 0; u < 2; ++u) {   // packed FADD2 / FMUL2: one instruction per two elements
             const int c = h2 * 32 + c4 * 4 + 2 * u;
-            const float2 nd = kDKV ? make_float2(-stat[c], -stat[c + 1]) : make_float2(-dr, -dr);
-            const float2 dv = fmul2(make_float2(pr[c], pr[c + 1]), fadd2(make_float2(dp[c4 * 4 + 2 * u], dp[c4 * 4 + 2 * u + 1]), nd));
+            const float2 dv = fmul2(make_float2(pr[c], pr[c + 1]),
+                                    fadd2(make_float2(dp[c4 * 4 + 2 * u], dp[c4 * 4 + 2 * u + 1]), make_float2(-dq[2 * u], -dq[2 * u + 1])));
             dk[h2 * 16 + c4 * 2 + u] = pack_16x2<kF16>(dv.x, dv.y);
           }
         }
       }
-      // dS over the first 32 of the thread's own 64 columns of dP (all 64 are in registers by now)
-      tmem_st32(tDP, dk);
+      // dS over the first half of the thread's own columns of dP (all of them have been read by now)
+      if constexpr (kBwdHalf == 64) tmem_st32(tDP, dk);
+      else tmem_st16(tDP, dk);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(bar_ds);
@@ -466,21 +499,24 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
     const int n_rows = kDKV ? p.n_k : p.n_q;
     auto store_acc = [&](uint32_t tcol, float mul, void* out, int64_t sb, int64_t sh, int64_t sn) {
       uint8_t* dst = static_cast<uint8_t*>(out) + 2 * (batch * sb + head_r * sh + static_cast<int64_t>(my_row) * sn);
+      constexpr int kCols = kHeadDim / kBwdSplit;          // accumulator columns per thread: [hh kCols, (hh + 1) kCols)
+      constexpr int kChunk = kCols < 32 ? kCols : 32;      // 32 or 16 columns per TMEM load
 #pragma unroll
-      for (int c2 = 0; c2 < kHeadDim / 64; ++c2) {
-        const int cc = hh * (kHeadDim / 64) + c2;   // 32-column chunk: thread hh of a lane takes columns [hh d/2, (hh + 1) d/2)
-        uint32_t v[32];
+      for (int c2 = 0; c2 < kCols / kChunk; ++c2) {
+        const int col0 = hh * kCols + c2 * kChunk;
+        uint32_t v[kChunk];
         if (have) {
-          tmem_ld32(tmem_base + lane_base + tcol + cc * 32, v);
+          if constexpr (kChunk == 32) tmem_ld32(tmem_base + lane_base + tcol + col0, v);
+          else tmem_ld16(tmem_base + lane_base + tcol + col0, v);
           tc_wait_ld();
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0u;
+          for (int i = 0; i < kChunk; ++i) v[i] = 0u;
         }
         if (my_row < n_rows) {
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int col = cc * 32 + q4 * 8;
+          for (int q4 = 0; q4 < kChunk / 8; ++q4) {
+            const int col = col0 + q4 * 8;
             if (col < p.head_dim) {
               uint4 pk;
               pk.x = pack_16x2<kF16>(__uint_as_float(v[q4 * 8 + 0]) * mul, __uint_as_float(v[q4 * 8 + 1]) * mul);
@@ -504,7 +540,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kBwdProdWarp) {
     __syncwarp();
     tmem_dealloc(tmem_base, 512);
   }
