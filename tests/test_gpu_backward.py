@@ -224,3 +224,19 @@ def test_forward_and_backward_under_cuda_graph_capture(fab, cuda_device):
     assert torch.equal(o_c, o_e)
     for a, b in zip(grads_c, grads_e):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n,causal", [(32768, True), (16384, False)])
+def test_backward_at_ring_scale_lengths_vs_blockwise_recomputation(fab, cuda_device, n, causal):
+    """Hundreds of streamed steps per CTA (N = 32768: 256) — lengths at which no N x N reference fits.  Checker: the blockwise
+    recomputation backward (torch matmuls in fp32 over row blocks; itself checked against float64 autograd by
+    test_autograd_backward_vs_torch_autograd on fp32 tensors), on the same O and LSE."""
+    from flashattention_c_b200.autograd import recompute_backward
+
+    q, k, v, do = (t.to(cuda_device) for t in _inputs(1, 2, 2, n, n, 128, torch.bfloat16, seed=n))
+    scale = 1.0 / math.sqrt(128)
+    o, lse = fab.attention(q, k, v, causal=causal, scale=scale, return_lse=True)
+    got = fab.attention_backward(q, k, v, o, lse, do, causal=causal, scale=scale)
+    want = recompute_backward(q, k, v, o, lse, do, causal, scale)
+    for name, a, b in zip(("dq", "dk", "dv"), got, want):
+        assert _rel(a, b) < TOL[torch.bfloat16], name
