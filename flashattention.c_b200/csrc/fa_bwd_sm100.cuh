@@ -251,7 +251,12 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
     // Order on the (in-order) tensor pipe:  S(0) dP(0) | then per step i:  [P(i)] dV(i)  S(i+1)  [dS(i)] dK(i)  dP(i+1)
     // (dQ launch: no dV; dK -> dQ).  S(i+1) overwrites the S columns once dV(i) has read P(i) out of them, dP(i+1) the dP columns
     // once dK(i) has read dS(i): the two 128-column regions are the double buffer, one contraction apart.
-    if (lane == 0 && n_steps > 0) {
+    // The whole warp follows the (warp-uniform) control flow and waits on the mbarriers; one elected lane issues.  (Issued from
+    // inside an `if (lane == 0)` region every tcgen05.mma is wrapped in an ELECT / branch loop of its own by the compiler — the
+    // operands of a warp-uniform instruction could differ between lanes for all it knows — and a step's 32 MMAs then issue more
+    // slowly than the tensor pipe retires them: profiles/r02_mma_probe_bwd_pattern.log has the pipe alone at 2078 cycles per step
+    // against 2700-2900 measured in the kernel.)
+    if (n_steps > 0) {
       constexpr uint32_t kFmt = kF16 ? 0u : 1u;
       constexpr uint32_t idesc_sd = make_idesc(kFmt, 0, kBwdRes, kBwdStr);      // S, dP: 128 x 128, both operands K-major
       constexpr uint32_t idesc_acc = make_idesc(kFmt, 1, kBwdRes, kHeadDim);    // accumulators: 128 x d, B MN-major
@@ -296,42 +301,56 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
                         (step > 0 || ks > 0) ? 1u : 0u);
       };
       wait_full(0, 0);
-      issue_rt(tS, r1d, 0, 0);
-      tc_commit(bar_s);
+      if (elect_one_sync()) {
+        issue_rt(tS, r1d, 0, 0);
+        tc_commit(bar_s);
+      }
+      __syncwarp();
       wait_full(0, 1);
-      issue_rt(tDP, r2d, 0, 1);
-      tc_commit(bar_dp);
-      if (!kDKV) tc_commit(bar_empty2);                    // dQ launch: V_0 is only read by dP(0)
+      if (elect_one_sync()) {
+        issue_rt(tDP, r2d, 0, 1);
+        tc_commit(bar_dp);
+        if (!kDKV) tc_commit(bar_empty2);                  // dQ launch: V_0 is only read by dP(0)
+      }
+      __syncwarp();
       for (int step = 0; step < n_steps; ++step) {
         const uint32_t par = static_cast<uint32_t>(step & 1);
-        FA_BWD_TRACE_AT(2, step, 0);
+        const bool more = step + 1 < n_steps;
+        if (lane == 0) FA_BWD_TRACE_AT(2, step, 0);
         mbar_wait(bar_p, par, TAG_B_P);
         tc_fence_after();
-        FA_BWD_TRACE_AT(2, step, 1);
-        if (kDKV) {
-          issue_acc(acc0, tS, step, 1);                    // dV += P^T dO
-          tc_commit(bar_empty2 + 8 * (step % T::kRing2));  // dO_i has been read by dP(i) and dV(i)
+        if (lane == 0) FA_BWD_TRACE_AT(2, step, 1);
+        if (more) wait_full(step + 1, 0);
+        if (elect_one_sync()) {
+          if (kDKV) {
+            issue_acc(acc0, tS, step, 1);                    // dV += P^T dO
+            tc_commit(bar_empty2 + 8 * (step % T::kRing2));  // dO_i has been read by dP(i) and dV(i)
+          }
+          if (more) {
+            issue_rt(tS, r1d, step + 1, 0);                  // S of the next step
+            tc_commit(bar_s);
+          }
         }
-        if (step + 1 < n_steps) {
-          wait_full(step + 1, 0);
-          issue_rt(tS, r1d, step + 1, 0);                  // S of the next step
-          tc_commit(bar_s);
-        }
-        FA_BWD_TRACE_AT(2, step, 2);
+        __syncwarp();
+        if (lane == 0) FA_BWD_TRACE_AT(2, step, 2);
         mbar_wait(bar_ds, par, TAG_B_DS);
         tc_fence_after();
-        FA_BWD_TRACE_AT(2, step, 3);
-        issue_acc(kDKV ? acc1 : acc0, tDP, step, 0);       // dK += dS^T Q   /   dQ += dS K
-        tc_commit(bar_empty1 + 8 * (step % T::kRing1));    // Q_i / K_j has been read by S and by dK / dQ once everything issued so far completes
-        if (step + 1 < n_steps) {
-          wait_full(step + 1, 1);
-          issue_rt(tDP, r2d, step + 1, 1);                 // dP of the next step
-          tc_commit(bar_dp);
-          if (!kDKV) tc_commit(bar_empty2 + 8 * ((step + 1) % T::kRing2));   // dQ launch: V_j is only read by dP(j)
+        if (lane == 0) FA_BWD_TRACE_AT(2, step, 3);
+        if (more) wait_full(step + 1, 1);
+        if (elect_one_sync()) {
+          issue_acc(kDKV ? acc1 : acc0, tDP, step, 0);       // dK += dS^T Q   /   dQ += dS K
+          tc_commit(bar_empty1 + 8 * (step % T::kRing1));    // Q_i / K_j has been read by S and by dK / dQ once everything issued so far completes
+          if (more) {
+            issue_rt(tDP, r2d, step + 1, 1);                 // dP of the next step
+            tc_commit(bar_dp);
+            if (!kDKV) tc_commit(bar_empty2 + 8 * ((step + 1) % T::kRing2));   // dQ launch: V_j is only read by dP(j)
+          }
         }
-        FA_BWD_TRACE_AT(2, step, 4);
+        __syncwarp();
+        if (lane == 0) FA_BWD_TRACE_AT(2, step, 4);
       }
-      tc_commit(bar_acc);
+      if (elect_one_sync()) tc_commit(bar_acc);
+      __syncwarp();
     }
   } else {
     // =========================== P, dS (two threads per TMEM lane) + epilogue ===========================

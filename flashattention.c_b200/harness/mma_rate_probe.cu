@@ -261,7 +261,99 @@ void run(const char* name) {
   cudaFree(d);
 }
 
-int main() {
+// ---- the backward kernel's MMA stream, alone on the SM: per step  TS (acc0 += P^T dO)  SS (S)  TS (acc1 += dS^T Q)  SS (dP)
+// (fa_bwd_sm100.cuh), one issuing thread, nothing else running.  order 0: as the kernel issues them (four switches between
+// SMEM- and TMEM-sourced A operands per step); 1: TS TS SS SS (two switches); 2: the SS groups only; 3: the TS groups only.
+// What does a step cost the tensor pipe by itself, and what does a switch cost?
+template <int kD>
+__global__ void __launch_bounds__(128, 1) probe_bwd_pattern(long long* out, int reps, int inner, int order) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sR = base, sT = base + 4 * 16384, bar = base + 8 * 16384, tptr = bar + 16;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  for (uint32_t i = threadIdx.x; i < 8 * 16384 / 4; i += blockDim.x) st_shared_b32(base + 4 * i, 0x3c003c00u);
+  fence_proxy_async_smem();
+  if (threadIdx.x < 32) {
+    tmem_alloc(tptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ld_shared_b32(tptr);
+  if (threadIdx.x == 0) {
+    constexpr uint32_t idesc_sd = make_idesc(1u, 0, 128, 128);
+    constexpr uint32_t idesc_acc = make_idesc(1u, 1, 128, kD);
+    constexpr uint64_t hi_k = make_sdesc_hi_sw128(16, 1024);
+    constexpr uint64_t hi_mn = make_sdesc_hi_sw128(16384, 1024);
+    constexpr int kStepsD = kD / 16;
+    auto ss = [&](uint32_t d) {
+#pragma unroll
+      for (int kk = 0; kk < kStepsD; ++kk) {
+        const uint32_t off16 = ((kk >> 2) * 16384 + (kk & 3) * 32) >> 4;
+        mma_ss<false>(d, sdesc_at(hi_k, sR) + off16, sdesc_at(hi_k, sT) + off16, idesc_sd, kk > 0 ? 1u : 0u);
+      }
+    };
+    auto ts = [&](uint32_t acc, uint32_t a) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        mma_ts<false>(acc, a + static_cast<uint32_t>((ks >> 2) * 64 + (ks & 3) * 8), sdesc_at(hi_mn, sT) + static_cast<uint32_t>(ks * 128), idesc_acc, 1u);
+    };
+    long long best = 1ll << 60;
+    uint32_t parity = 0;
+    for (int r = 0; r < reps; ++r) {
+      const long long t0 = clock64();
+      for (int it = 0; it < inner; ++it) {
+        if (order == 0) { ts(tmem + 256, tmem); ss(tmem); ts(tmem + 256 + kD, tmem + 128); ss(tmem + 128); }
+        else if (order == 1) { ts(tmem + 256, tmem); ts(tmem + 256 + kD, tmem + 128); ss(tmem); ss(tmem + 128); }
+        else if (order == 2) { ss(tmem); ss(tmem + 128); }
+        else { ts(tmem + 256, tmem); ts(tmem + 256 + kD, tmem + 128); }
+      }
+      tc_commit(bar);
+      mbar_wait(bar, parity, 99);
+      parity ^= 1;
+      const long long dt = clock64() - t0;
+      best = dt < best ? dt : best;
+    }
+    out[0] = best;
+    out[1] = inner;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+template <int kD>
+void run_bwd_pattern(int order, const char* what) {
+  long long* d;
+  cudaMalloc(&d, 16);
+  auto k = probe_bwd_pattern<kD>;
+  const int smem = 8 * 16384 + 1024 + 64;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  k<<<1, 128, smem>>>(d, 5, 8, order);
+  long long h[2] = {0, 0};
+  cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { printf("bwd pattern: %s\n", cudaGetErrorString(e)); exit(1); }
+  printf("{\"probe\": \"backward MMA stream d=%d, %s\", \"steps\": %lld, \"cycles\": %lld, \"cycles_per_step\": %.1f}\n", kD, what, h[1], h[0],
+         (double)h[0] / h[1]);
+  fflush(stdout);
+  cudaFree(d);
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 'b') {   // only the backward-pattern probes
+    run_bwd_pattern<128>(0, "TS SS TS SS (as issued: 16 TS + 16 SS MMAs per step)");
+    run_bwd_pattern<128>(1, "TS TS SS SS");
+    run_bwd_pattern<128>(2, "SS groups only (16 MMAs)");
+    run_bwd_pattern<128>(3, "TS groups only (16 MMAs)");
+    run_bwd_pattern<64>(0, "TS SS TS SS (as issued: 16 TS N=64 + 8 SS MMAs per step)");
+    run_bwd_pattern<64>(1, "TS TS SS SS");
+    run_bwd_pattern<64>(2, "SS groups only (8 MMAs)");
+    run_bwd_pattern<64>(3, "TS groups only (16 MMAs, N = 64)");
+    return 0;
+  }
   run<true, false, 128>("tf32 SS 128x128x8  (S = Q K^T as shipped)");
   run<true, true, 128>("tf32 TS 128x128x8  (Q from TMEM)");
   run<true, true, 64>("tf32 TS 128x64x8   (P V, d = 64)");
