@@ -53,11 +53,19 @@
 // (ptx.cuh: exp2_poly2, relative error 7.5e-5 — P is rounded to 16 bits right after) instead of MUFU.EX2: both launches evaluate
 // every P element, 16384 per 128 x 128 step at 16 per clock, and the traces show the exp pass, not the tensor pipe, setting the
 // step time (profiles/r02_bwd_trace_v3_stream128.txt).
+// Per launch, by ncu durations (profiles/r02_bwd_ab_poly_fraction_ncu.log): the dK/dV launch is fastest at 1/2, the dQ launch
+// (which has no P to pack and store, so fewer instructions per element to begin with) at 1/4 - 3/8.
 #ifndef FA_BWD_POLY_NUM
 #define FA_BWD_POLY_NUM 1
 #endif
 #ifndef FA_BWD_POLY_DEN
 #define FA_BWD_POLY_DEN 2
+#endif
+#ifndef FA_BWD_POLY_NUM_DQ
+#define FA_BWD_POLY_NUM_DQ 3
+#endif
+#ifndef FA_BWD_POLY_DEN_DQ
+#define FA_BWD_POLY_DEN_DQ 8
 #endif
 
 namespace fa {
@@ -317,10 +325,15 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         const uint32_t par = static_cast<uint32_t>(step & 1);
         const bool more = step + 1 < n_steps;
         if (lane == 0) FA_BWD_TRACE_AT(2, step, 0);
+        // the next step's tiles were requested one to two steps ago: check for them now, while the pipe is still busy with what
+        // was issued last, so that nothing stands between a P / dS hand-over and the issue that waits for it
+        if (more) {
+          wait_full(step + 1, 0);
+          wait_full(step + 1, 1);
+        }
         mbar_wait(bar_p, par, TAG_B_P);
         tc_fence_after();
         if (lane == 0) FA_BWD_TRACE_AT(2, step, 1);
-        if (more) wait_full(step + 1, 0);
         if (elect_one_sync()) {
           if (kDKV) {
             issue_acc(acc0, tS, step, 1);                    // dV += P^T dO
@@ -336,7 +349,6 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         mbar_wait(bar_ds, par, TAG_B_DS);
         tc_fence_after();
         if (lane == 0) FA_BWD_TRACE_AT(2, step, 3);
-        if (more) wait_full(step + 1, 1);
         if (elect_one_sync()) {
           issue_acc(kDKV ? acc1 : acc0, tDP, step, 0);       // dK += dS^T Q   /   dQ += dS K
           tc_commit(bar_empty1 + 8 * (step % T::kRing1));    // Q_i / K_j has been read by S and by dK / dQ once everything issued so far completes
@@ -442,7 +454,8 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
           for (int u = 0; u < 2; ++u) {
             const int i = c4 * 2 + u;   // pair index: columns 2 i, 2 i + 1
             float2 e = ffma2(make_float2(pr[2 * i], pr[2 * i + 1]), make_float2(p.scale_log2, p.scale_log2), make_float2(-lq[2 * u], -lq[2 * u + 1]));
-            if ((i % FA_BWD_POLY_DEN) < FA_BWD_POLY_NUM) {
+            constexpr int kPolyNum = kDKV ? FA_BWD_POLY_NUM : FA_BWD_POLY_NUM_DQ, kPolyDen = kDKV ? FA_BWD_POLY_DEN : FA_BWD_POLY_DEN_DQ;
+            if ((i % kPolyDen) < kPolyNum) {
               e = exp2_poly2(e);
             } else {
               e.x = ex2(e.x);
