@@ -335,10 +335,7 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         tc_fence_after();
         if (lane == 0) FA_BWD_TRACE_AT(2, step, 1);
         if (elect_one_sync()) {
-          if (kDKV) {
-            issue_acc(acc0, tS, step, 1);                    // dV += P^T dO
-            tc_commit(bar_empty2 + 8 * (step % T::kRing2));  // dO_i has been read by dP(i) and dV(i)
-          }
+          if (kDKV) issue_acc(acc0, tS, step, 1);            // dV += P^T dO
           if (more) {
             issue_rt(tS, r1d, step + 1, 0);                  // S of the next step
             tc_commit(bar_s);
@@ -352,6 +349,11 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         if (elect_one_sync()) {
           issue_acc(kDKV ? acc1 : acc0, tDP, step, 0);       // dK += dS^T Q   /   dQ += dS K
           tc_commit(bar_empty1 + 8 * (step % T::kRing1));    // Q_i / K_j has been read by S and by dK / dQ once everything issued so far completes
+          // dO_i's ring slot also carries D[i], which the element-wise warps read AFTER they have handed P(i) over — i.e. possibly
+          // after dV(i), the tile's last reader on the tensor pipe, has been issued.  It is therefore released here, behind dK(i):
+          // dK(i) needs dS(i), and dS(i) is written after D[i] has been read.  (Released behind dV(i), a slow warp could find the
+          // statistics of step i + 2 in the slot: found by running the tests under compute-sanitizer, which stretches such windows.)
+          if (kDKV) tc_commit(bar_empty2 + 8 * (step % T::kRing2));
           if (more) {
             issue_rt(tDP, r2d, step + 1, 1);                 // dP of the next step
             tc_commit(bar_dp);

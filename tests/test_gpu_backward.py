@@ -240,3 +240,24 @@ def test_backward_at_ring_scale_lengths_vs_blockwise_recomputation(fab, cuda_dev
     want = recompute_backward(q, k, v, o, lse, do, causal, scale)
     for name, a, b in zip(("dq", "dk", "dv"), got, want):
         assert _rel(a, b) < TOL[torch.bfloat16], name
+
+
+def test_backward_under_compute_sanitizer_timing_stretch():
+    """The bring-up cases (incl. grouped K/V heads with more streamed steps than ring slots) under compute-sanitizer memcheck: no
+    memory error, and — because the tool stretches every window between a hand-over and its consumer — still the right
+    numbers.  This is the run that exposed a ring slot being released one contraction too early (its per-row statistics were read
+    by the element-wise warps after the tile's last reader on the tensor pipe had been issued): correct at full speed, wrong dK
+    under the sanitizer."""
+    import shutil
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    tool = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if not Path(tool).exists():
+        pytest.skip("compute-sanitizer not installed")
+    root = Path(__file__).resolve().parents[1]
+    r = subprocess.run([tool, "--tool", "memcheck", "--error-exitcode", "9", sys.executable, str(root / "scripts" / "bwd_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "BAD 0" in r.stdout and "ERROR SUMMARY: 0 errors" in r.stdout
