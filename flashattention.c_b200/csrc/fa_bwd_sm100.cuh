@@ -112,6 +112,12 @@ struct BwdTraits {
   // of the second (dO / V) is done with much earlier and two are enough.  At d = 128 that is 64 + 96 + 64 KB: all of SMEM.
   static constexpr int kRing1 = kDChunks == 1 ? 4 : 3;
   static constexpr int kRing2 = kDChunks == 1 ? 3 : 2;
+  // D[i] rides in dO_i's ring slot and is read by the element-wise warps.  With a two-deep ring (d = 128) the slot must go back
+  // to the producer right behind dV(i), so the warps take D[i] into registers BEFORE they hand P(i) over (which is what lets
+  // dV(i) be issued); with three slots (d = 64) they read it after the hand-over — off the P chain — and the slot is released
+  // one contraction later, behind dK(i) (ncu durations, profiles/r02_bwd_ab_stat_release_ncu.log: each choice is 4-5 % faster
+  // than the other on its instance).
+  static constexpr bool kEarlyD = kBwdStatRegs && kRing2 == 2;
   static constexpr int kStatBytes = kBwdStr * 4;                 // LSE2[128] (rides with ring 1) or D[128] (ring 2) of a (Q, dO) tile
   static constexpr int kNumBarriers = 1 + 2 * kRing1 + 2 * kRing2 + 4 + 1;
   // (the dynamic SMEM window is 1024-byte aligned — checked at kernel entry — so there is no alignment slack: there is no room for it)
@@ -335,7 +341,12 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         tc_fence_after();
         if (lane == 0) FA_BWD_TRACE_AT(2, step, 1);
         if (elect_one_sync()) {
-          if (kDKV) issue_acc(acc0, tS, step, 1);            // dV += P^T dO
+          if (kDKV) {
+            issue_acc(acc0, tS, step, 1);                    // dV += P^T dO
+            // dO_i has been read by dP(i) and dV(i).  D[i] rides in the same ring slot and is read by the element-wise warps: with
+            // kEarlyD they have it in registers before they hand P(i) over, and the slot goes back to the producer behind dV(i)
+            if (T::kEarlyD) tc_commit(bar_empty2 + 8 * (step % T::kRing2));
+          }
           if (more) {
             issue_rt(tS, r1d, step + 1, 0);                  // S of the next step
             tc_commit(bar_s);
@@ -349,11 +360,9 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         if (elect_one_sync()) {
           issue_acc(kDKV ? acc1 : acc0, tDP, step, 0);       // dK += dS^T Q   /   dQ += dS K
           tc_commit(bar_empty1 + 8 * (step % T::kRing1));    // Q_i / K_j has been read by S and by dK / dQ once everything issued so far completes
-          // dO_i's ring slot also carries D[i], which the element-wise warps read AFTER they have handed P(i) over — i.e. possibly
-          // after dV(i), the tile's last reader on the tensor pipe, has been issued.  It is therefore released here, behind dK(i):
-          // dK(i) needs dS(i), and dS(i) is written after D[i] has been read.  (Released behind dV(i), a slow warp could find the
-          // statistics of step i + 2 in the slot: found by running the tests under compute-sanitizer, which stretches such windows.)
-          if (kDKV) tc_commit(bar_empty2 + 8 * (step % T::kRing2));
+          // (!kEarlyD: D[i] is read after the P hand-over, possibly after dV(i) has been issued, so dO_i's slot is released behind
+          // dK(i), which needs dS(i), which is written after D[i] has been read)
+          if (kDKV && !T::kEarlyD) tc_commit(bar_empty2 + 8 * (step % T::kRing2));
           if (more) {
             issue_rt(tDP, r2d, step + 1, 1);                 // dP of the next step
             tc_commit(bar_dp);
@@ -476,6 +485,15 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
       else exp_pass(std::false_type{});
       if (tracer) FA_BWD_TRACE_AT(hh, step, 1);
       if (kDKV) {
+        // kEarlyD: D[i] into the registers LSE2[i] has just left — BEFORE P(i) is handed over: the hand-over lets the MMA warp issue dV(i),
+        // the last reader of dO_i on the tensor pipe, behind which the ring slot that also holds D[i] returns to the producer.
+        // (Read after the hand-over, a slow warp could find the statistics of step i + 2 in the slot: correct at full speed,
+        // wrong dK under compute-sanitizer, which stretches such windows — tests/test_gpu_backward.py runs that check.)
+        // The loads complete under the packing and the TMEM store of P; the empty asm below makes the arrive wait for them.
+        if (T::kEarlyD) {
+          mbar_wait(bar_full2 + 8 * s2, (step / T::kRing2) & 1, TAG_B_FULL);
+          load_stats(s_d);
+        }
         // P^T (two 16-bit values per column) goes over the first half of the thread's OWN columns of S, which it has in registers
         uint32_t pk[kBwdHalf / 2];
 #pragma unroll
@@ -484,10 +502,14 @@ fa_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tm_r1, const __grid_cons
         else tmem_st16(tS, pk);
         tc_wait_st();
         tc_fence_before();
+        if constexpr (T::kEarlyD) {
+#pragma unroll
+          for (int i = 0; i < kBwdHalf; ++i) asm volatile("" ::"f"(stat[i]) : "memory");   // (keeps the loads ahead of the arrive)
+        }
         mbar_arrive(bar_p);
       }
       if (tracer) FA_BWD_TRACE_AT(hh, step, 2);
-      if (kDKV) {
+      if (kDKV && !T::kEarlyD) {
         mbar_wait(bar_full2 + 8 * s2, (step / T::kRing2) & 1, TAG_B_FULL);
         load_stats(s_d);
       }
