@@ -125,7 +125,12 @@
 #define FA_STEP_UNROLL _Pragma("unroll")
 #endif
 #ifndef FA_OPT_SPLIT_KEYS
-#define FA_OPT_SPLIT_KEYS 64  // (96 measured 2-3% slower: profiles/r01_ab_tf32_comp.log) P is handed to the MMA warp in two pieces: keys [0, FA_OPT_SPLIT_KEYS) and the rest (64 or 96)
+#define FA_OPT_SPLIT_KEYS 64  // P is handed to the MMA warp in two pieces: keys [0, FA_OPT_SPLIT_KEYS) and the rest (64 or 96).  16-bit instances
+#endif
+#ifndef FA_OPT_SPLIT_KEYS_TF32
+#define FA_OPT_SPLIT_KEYS_TF32 96   // tf32 instances.  By ncu launch durations (profiles/r02_fwd_ab_knobs_ncu.log): 96 is 1 % (C2) to 2.5 % (C3)
+                                    // faster than 64 on the tf32 instances and 1.9 % slower on bf16 d = 128 (the event-timed A/B of round 1,
+                                    // profiles/r01_ab_tf32_comp.log, could not resolve this)
 #endif
 // Of every FA_POLY_DEN_x consecutive element pairs of a P row, the first FA_POLY_NUM_x get exp2 from the FMA-pipe
 // polynomial (packed FFMA2/FADD2) instead of MUFU.EX2: the softmax is MUFU-bound (16 ex2/clk/SM), the polynomial moves part
@@ -247,7 +252,7 @@ struct FwdTraits {
   static constexpr int kQSets = kTileChunks == 1 ? 2 : 1;      // Q double-buffered across items where SMEM allows
   static constexpr bool kComp = kTF32 && !kPrecise && (FA_OPT_TF32_COMP != 0);   // tf32 truncation compensated instead of reproduced
   static constexpr bool kPacked = (FA_OPT_F2 != 0) && (!kTF32 || kComp || kPrecise);   // FFMA2 / FADD2 forms in the exp loop
-  static constexpr int kSplitKeys = FA_OPT_SPLIT_KEYS;
+  static constexpr int kSplitKeys = kTF32 ? FA_OPT_SPLIT_KEYS_TF32 : FA_OPT_SPLIT_KEYS;
   static_assert(kSplitKeys == 64 || kSplitKeys == 96, "P split point");
   // polynomial exp2 on kPolyNum of every kPolyDen element pairs (packed path only; never in a precise instance: its 7.5e-5
   // relative error is what that mode exists to avoid)
