@@ -229,8 +229,8 @@ def test_forward_and_backward_under_cuda_graph_capture(fab, cuda_device):
 @pytest.mark.parametrize("n,causal", [(32768, True), (16384, False)])
 def test_backward_at_ring_scale_lengths_vs_blockwise_recomputation(fab, cuda_device, n, causal):
     """Hundreds of streamed steps per CTA (N = 32768: 256) — lengths at which no N x N reference fits.  Checker: the blockwise
-    recomputation backward (torch matmuls in fp32 over row blocks; itself checked against float64 autograd by
-    test_autograd_backward_vs_torch_autograd on fp32 tensors), on the same O and LSE."""
+    recomputation backward (torch matmuls in fp32 over row blocks; itself checked against the fp64 oracle on CPU tensors by
+    tests/test_oracle.py::test_blockwise_recomputation_backward_matches_the_fp64_oracle), on the same O and LSE."""
     from flashattention_c_b200.autograd import recompute_backward
 
     q, k, v, do = (t.to(cuda_device) for t in _inputs(1, 2, 2, n, n, 128, torch.bfloat16, seed=n))

@@ -125,3 +125,23 @@ def test_backward_oracle_matches_central_differences(oracle, causal, hk, nq, nk)
             x[idx] = old
             num[idx] = (up - dn) / (2 * eps)
         assert np.abs(num - gx).max() < 1e-6 * max(1.0, np.abs(gx).max()), name
+
+
+@pytest.mark.parametrize("causal,nq,nk", [(False, 40, 56), (True, 48, 48), (True, 30, 50), (True, 50, 30)])
+def test_blockwise_recomputation_backward_matches_the_fp64_oracle(oracle, causal, nq, nk):
+    """`autograd.recompute_backward` (plain torch matmuls over row blocks: the gradient path of fp32 tensors and the checker of the
+    backward kernels at lengths no N x N reference fits) against backward_f64, on CPU tensors from the forward oracle's O and LSE."""
+    import torch
+
+    from flashattention_c_b200.autograd import recompute_backward
+
+    rng = np.random.default_rng(11)
+    B, H, d, scale = 2, 3, 16, 0.25
+    q, do = (rng.standard_normal((B, H, nq, d)).astype(np.float32) for _ in range(2))
+    k, v = (rng.standard_normal((B, H, nk, d)).astype(np.float32) for _ in range(2))
+    o, lse = oracle.numpy_f64(q, k, v, scale=scale, causal=causal)
+    got = recompute_backward(*(torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)) for t in (q, k, v, o)),
+                             torch.from_numpy(lse.astype(np.float32)), torch.from_numpy(do), causal, scale)
+    want = oracle.backward_f64(q, k, v, do, scale=scale, causal=causal)
+    for name, g, w in zip(("dq", "dk", "dv"), got, want):
+        assert np.abs(g.numpy() - w).max() < 2e-5 * max(1.0, np.abs(w).max()), name
